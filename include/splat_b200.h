@@ -1,0 +1,161 @@
+/*
+ * splat_b200.h -- C ABI of libsplat_b200.so: the drop-in boundary for splatapult's splat hot path.
+ *
+ * The reference (hyperlogic/splatapult) has no plugin/FFI layer: the boundary is two C++ classes,
+ *   GaussianCloud  src/gaussiancloud.h:17-91
+ *   SplatRenderer  src/splatrenderer.h:23-67
+ * called from App::Init (src/app.cpp:549-559) and App::Render (src/app.cpp:1067-1068).  Each entry point
+ * below names the reference member it stands in for.  The C++ classes with the reference's own method
+ * names live in include/splatapult_b200/{gaussiancloud,splatrenderer}.h and are thin owners of these
+ * handles' implementation; INTEGRATION.md shows the patch a splatapult maintainer would apply.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no C++/torch types.
+ *   - every int-returning call: 0 = ok, negative = error (spl_last_error() holds the message, per thread).
+ *   - matrices are glm-layout column-major float[16]; cameraMat is camera-to-world (the renderer inverts it,
+ *     src/splatrenderer.cpp:161,327); viewport = (x, y, width, height) with x = y = 0;
+ *     nearFar must equal the near/far baked into projMat.
+ *   - sort/render are asynchronous on the renderer's CUDA stream; there is no host sync on the frame path
+ *     (the reference stalls on a counter read-back, src/splatrenderer.cpp:195-204).
+ *   - the framebuffer is GL-oriented: row 0 is the BOTTOM row, pixel centres at (i+0.5, j+0.5), RGBA,
+ *     alpha == 1 (clear colour (0,0,0,1) + "over" blending, src/app.cpp:153-160).
+ *   - there is NO CPU fallback: without a CUDA device every renderer call fails with SPL_ERR_CUDA.
+ */
+#ifndef SPLAT_B200_H
+#define SPLAT_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(_WIN32)
+#define SPL_API __declspec(dllexport)
+#else
+#define SPL_API __attribute__((visibility("default")))
+#endif
+
+typedef struct spl_cloud spl_cloud;       /* GaussianCloud  */
+typedef struct spl_renderer spl_renderer; /* SplatRenderer  */
+typedef struct spl_sorter spl_sorter;     /* stand-alone (tile|depth) u64 radix sorter */
+
+enum {
+    SPL_OK = 0,
+    SPL_ERR_ARG = -1,      /* bad argument / state */
+    SPL_ERR_IO = -2,       /* file open / parse failure (GaussianCloud::ImportPly returns false) */
+    SPL_ERR_CUDA = -3,     /* CUDA runtime error or no device */
+    SPL_ERR_OVERFLOW = -4, /* tile-instance capacity exceeded (see spl_renderer_stats) */
+    SPL_ERR_ALLOC = -5
+};
+
+enum { SPL_FB_FP32 = 0 /* GL_RGBA32F, --fp32 */, SPL_FB_FP16 = 1 /* GL_RGBA16F, --fp16 */ }; /* src/app.cpp:1000-1035 */
+
+/* attribute ids for spl_cloud_attrib: the 16 BinaryAttribute accessors, src/gaussiancloud.h:42-57 */
+enum {
+    SPL_ATTR_POS_WITH_ALPHA = 0,
+    SPL_ATTR_R_SH0, SPL_ATTR_R_SH1, SPL_ATTR_R_SH2, SPL_ATTR_R_SH3,
+    SPL_ATTR_G_SH0, SPL_ATTR_G_SH1, SPL_ATTR_G_SH2, SPL_ATTR_G_SH3,
+    SPL_ATTR_B_SH0, SPL_ATTR_B_SH1, SPL_ATTR_B_SH2, SPL_ATTR_B_SH3,
+    SPL_ATTR_COV3_COL0, SPL_ATTR_COV3_COL1, SPL_ATTR_COV3_COL2,
+    SPL_ATTR_COUNT
+};
+
+SPL_API const char* spl_last_error(void);
+SPL_API int spl_version(void);
+SPL_API int spl_device_count(void); /* 0 when no CUDA device is usable */
+
+/* ---------------------------------------------------------------- GaussianCloud (host, src/gaussiancloud.h) */
+SPL_API spl_cloud* spl_cloud_create(int import_full_sh, int export_full_sh);           /* GaussianCloud(Options) :26 */
+SPL_API void spl_cloud_destroy(spl_cloud*);
+SPL_API int spl_cloud_import_ply(spl_cloud*, const char* ply_filename);                /* ImportPly :28 */
+SPL_API int spl_cloud_export_ply(const spl_cloud*, const char* ply_filename);          /* ExportPly :29 */
+SPL_API int spl_cloud_init_debug_cloud(spl_cloud*);                                    /* InitDebugCloud :31 */
+SPL_API int spl_cloud_prune_splats(spl_cloud*, const float origin[3], uint32_t count); /* PruneSplats :34 */
+/* adopt a copy of a caller-built AoS in the reference layout (stride 100 or 244 bytes) */
+SPL_API int spl_cloud_set_raw(spl_cloud*, const void* aos, size_t num_gaussians, size_t stride, int has_full_sh);
+SPL_API size_t spl_cloud_num_gaussians(const spl_cloud*);                              /* GetNumGaussians :36 */
+SPL_API size_t spl_cloud_stride(const spl_cloud*);                                     /* GetStride :37 */
+SPL_API size_t spl_cloud_total_size(const spl_cloud*);                                 /* GetTotalSize :38 */
+SPL_API void* spl_cloud_raw_data(spl_cloud*);                                          /* GetRawDataPtr :39 */
+SPL_API int spl_cloud_has_full_sh(const spl_cloud*);                                   /* HasFullSH :62 */
+/* BinaryAttribute {type,size,offset}; type 0 = Unknown, 7 = Float (src/core/binaryattribute.h:15-27) */
+SPL_API int spl_cloud_attrib(const spl_cloud*, int attr_id, int* type, size_t* size, size_t* offset);
+
+/* ---------------------------------------------------------------- SplatRenderer (src/splatrenderer.h) */
+SPL_API spl_renderer* spl_renderer_create(void);                                       /* SplatRenderer() :26 */
+SPL_API void spl_renderer_destroy(spl_renderer*);
+/* optional, before init: CUDA device ordinal, framebuffer format, and an external cudaStream_t to run on
+ * (NULL = the renderer creates its own non-blocking stream). */
+SPL_API int spl_renderer_configure(spl_renderer*, int device, int fb_format, void* cuda_stream);
+/* Init :29-30.  Copies the cloud to the device and packs it; keeps no reference to host memory. */
+SPL_API int spl_renderer_init(spl_renderer*, const spl_cloud*, int is_framebuffer_srgb_enabled, int use_rgc_sort_override);
+/* same, from an AoS that is already in device memory (e.g. the destination of an NCCL broadcast) */
+SPL_API int spl_renderer_init_device_aos(spl_renderer*, const void* device_aos, size_t num_gaussians, size_t stride,
+                                         int has_full_sh, int is_framebuffer_srgb_enabled);
+/* Sort :32-33: cull + project + SH + (tile|depth) key emission + device-wide radix sort + tile ranges */
+SPL_API int spl_renderer_sort(spl_renderer*, const float camera_mat[16], const float proj_mat[16],
+                              const float viewport[4], const float near_far[2]);
+/* Render :36-37: clears the target to (0,0,0,1) and composites the sorted lists front to back */
+SPL_API int spl_renderer_render(spl_renderer*, const float camera_mat[16], const float proj_mat[16],
+                                const float viewport[4], const float near_far[2]);
+/* the render target of the last Render (device pointer; valid until the next Render / resize / destroy) */
+SPL_API int spl_renderer_framebuffer(spl_renderer*, void** device_ptr, int* width, int* height,
+                                     size_t* row_pitch_bytes, int* fb_format);
+/* device->host copy of the target: enqueue on the renderer stream (host should be pinned) ... */
+SPL_API int spl_renderer_read_framebuffer_async(spl_renderer*, void* host, size_t bytes);
+/* ... or copy and wait; re-runs the frame once with a larger capacity if it overflowed */
+SPL_API int spl_renderer_read_framebuffer(spl_renderer*, void* host, size_t bytes);
+SPL_API int spl_renderer_synchronize(spl_renderer*);
+
+typedef struct spl_stats {
+    uint64_t num_gaussians;    /* N */
+    uint64_t num_visible;      /* V: gaussians that pass K1+K6 (the reference's sortCount after the geometry cull) */
+    uint64_t num_instances;    /* D: (gaussian,tile) keys emitted this frame */
+    uint64_t instance_capacity;
+    uint32_t overflow;         /* 1 if D exceeded capacity (frame incomplete; call spl_renderer_reserve) */
+    uint32_t tiles_x, tiles_y, tile_size;
+    uint32_t sort_passes, sort_bits;
+    uint32_t sh_mode;          /* 0 = DC only, 1 = degree 1 (base layout), 3 = degree 3 (FULL_SH) */
+    uint32_t kernel_launches;  /* kernels launched by the last Sort+Render */
+    float stage_ms[8];         /* when profiling is on: project, histogram, sort, ranges, composite, 0,0, total */
+} spl_stats;
+SPL_API int spl_renderer_stats(spl_renderer*, spl_stats* out); /* synchronizes the stream */
+SPL_API int spl_renderer_reserve(spl_renderer*, uint64_t instance_capacity);
+
+enum {
+    SPL_OPT_EARLY_OUT_T = 0,  /* stop a pixel when its transmittance drops below this (default 1e-4; 0 = exact) */
+    SPL_OPT_PROFILE = 1,      /* 1: bracket stages with CUDA events (stage_ms) */
+    SPL_OPT_INSTANCES_PER_GAUSSIAN = 2 /* initial capacity factor, before init (default 16) */
+};
+SPL_API int spl_renderer_set_option(spl_renderer*, int option, double value);
+
+/* parity-test taps: copy an intermediate buffer of the last frame to the host (synchronizes) */
+enum {
+    SPL_TAP_RECORDS = 0,    /* N x 48 B projected records {px,py,i00,i01,i10,i11,r,g,b,alpha,key,visible} */
+    SPL_TAP_KEYS = 1,       /* D x u64 sorted (tile<<32 | key) */
+    SPL_TAP_VALS = 2,       /* D x u32 sorted gaussian ids */
+    SPL_TAP_TILE_RANGES = 3 /* tiles x {u32 begin, u32 end} */
+};
+SPL_API int spl_renderer_tap(spl_renderer*, int what, void* host, size_t bytes);
+
+/* ---------------------------------------------------------------- stand-alone u64|u32 radix sort */
+SPL_API spl_sorter* spl_sorter_create(int device, uint64_t capacity);
+SPL_API void spl_sorter_destroy(spl_sorter*);
+/* stable ascending LSD sort of n (u64 key, u32 val) pairs on bits [begin_bit, end_bit); device pointers;
+ * result lands in (keys_out, vals_out) which must not alias the inputs (inputs are clobbered). */
+SPL_API int spl_sorter_sort(spl_sorter*, void* d_keys_in, void* d_vals_in, void* d_keys_out, void* d_vals_out,
+                            uint64_t n, int begin_bit, int end_bit, void* cuda_stream);
+/* convenience for tests: host arrays in, host arrays out */
+SPL_API int spl_sort_pairs_host(const uint64_t* keys, const uint32_t* vals, uint64_t n, int begin_bit, int end_bit,
+                                uint64_t* keys_out, uint32_t* vals_out);
+
+/* pinned host memory for the end-to-end path */
+SPL_API void* spl_host_alloc(size_t bytes);
+SPL_API void spl_host_free(void*);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SPLAT_B200_H */

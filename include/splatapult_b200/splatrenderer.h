@@ -1,0 +1,64 @@
+// splatrenderer.h -- B200-native drop-in for the reference's SplatRenderer (src/splatrenderer.h:23-67).
+//
+// Same call protocol as the reference: Init once with the cloud, then per frame Sort(...) followed by
+// Render(...) with identical arguments (src/app.cpp:1067-1068).  The OpenGL pipeline behind those calls
+// (presort_compute + multi_radixsort + splat_vert/geom/frag + ROP blending) is replaced by CUDA kernels
+// for sm_100a; the output is an explicit float framebuffer instead of "whatever GL target is bound".
+#pragma once
+#include <cstddef>
+#include <cstdint>
+#include <memory>
+#include <string>
+
+#include "gaussiancloud.h"
+#include "splatmath.h"
+
+struct spl_stats;
+
+namespace splat { struct RendererImpl; }
+
+class SplatRenderer
+{
+public:
+    enum class FrameBuffer { Float = 0 /* --fp32, GL_RGBA32F */, HalfFloat = 1 /* --fp16, GL_RGBA16F */ };
+
+    SplatRenderer();
+    ~SplatRenderer();
+    SplatRenderer(const SplatRenderer&) = delete;
+    SplatRenderer& operator=(const SplatRenderer&) = delete;
+
+    // optional, before Init: device ordinal, target format, external cudaStream_t (nullptr = own stream)
+    bool Configure(int device, FrameBuffer format, void* cudaStream = nullptr);
+
+    // reference signature (src/splatrenderer.h:29-30).  useRgcSortOverrideIn selected the reference's
+    // fallback GLSL sorter; both sorters produce the same stable order, so it is accepted and ignored.
+    bool Init(std::shared_ptr<GaussianCloud> gaussianCloud, bool isFramebufferSRGBEnabledIn, bool useRgcSortOverrideIn);
+    // same, from a reference-layout AoS already resident on the device (NCCL broadcast destination)
+    bool InitFromDevice(const void* deviceAos, size_t numGaussians, size_t stride, bool hasFullSH, bool isFramebufferSRGBEnabledIn);
+
+    // reference signatures (src/splatrenderer.h:32-37); viewport = (x, y, width, height)
+    void Sort(const splat::mat4& cameraMat, const splat::mat4& projMat, const splat::vec4& viewport, const splat::vec2& nearFar);
+    void Render(const splat::mat4& cameraMat, const splat::mat4& projMat, const splat::vec4& viewport, const splat::vec2& nearFar);
+
+    // --- explicit replacements for the reference's implicit GL state ---
+    bool GetFramebuffer(void** devicePtr, int* width, int* height, size_t* rowPitchBytes, FrameBuffer* format) const;
+    bool ReadFramebufferAsync(void* host, size_t bytes);
+    bool ReadFramebuffer(void* host, size_t bytes);  // waits; transparently re-renders once on capacity overflow
+    bool Synchronize();
+    bool GetStats(spl_stats* out);
+    bool Reserve(uint64_t instanceCapacity);
+    bool SetOption(int option, double value);
+    bool Tap(int what, void* host, size_t bytes);
+
+    int LastStatus() const { return status; }            // 0 or a negative SPL_ERR_* of the last call
+    const std::string& LastError() const { return error; }
+
+public:
+    // kept for source compatibility (src/splatrenderer.h:39); the CUDA sort has no such tuning knob
+    uint32_t numBlocksPerWorkgroup = 1024;
+
+protected:
+    std::unique_ptr<splat::RendererImpl> impl;
+    int status = 0;
+    std::string error;
+};

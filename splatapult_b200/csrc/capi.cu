@@ -1,0 +1,316 @@
+// capi.cu -- extern "C" surface of libsplat_b200.so (include/splat_b200.h): plain handles over the C++ classes.
+#include <cstring>
+#include <memory>
+#include <new>
+#include <string>
+
+#include "kernels.h"
+#include "splat_b200.h"
+#include "splatapult_b200/gaussiancloud.h"
+#include "splatapult_b200/splatrenderer.h"
+
+struct spl_cloud
+{
+    std::shared_ptr<GaussianCloud> gc;
+};
+struct spl_renderer
+{
+    SplatRenderer r;
+};
+
+namespace
+{
+thread_local std::string g_lastError;
+int set_error(int code, const std::string& msg)
+{
+    g_lastError = msg;
+    return code;
+}
+int from_renderer(spl_renderer* h, bool okFlag)
+{
+    if (okFlag) return SPL_OK;
+    g_lastError = h->r.LastError();
+    return h->r.LastStatus() ? h->r.LastStatus() : SPL_ERR_ARG;
+}
+}  // namespace
+
+extern "C" {
+
+const char* spl_last_error(void) { return g_lastError.c_str(); }
+int spl_version(void) { return 100; }
+int spl_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+// ------------------------------------------------------------------ cloud
+spl_cloud* spl_cloud_create(int import_full_sh, int export_full_sh)
+{
+    spl_cloud* c = new (std::nothrow) spl_cloud;
+    if (!c) return nullptr;
+    GaussianCloud::Options opt{import_full_sh != 0, export_full_sh != 0};
+    c->gc = std::make_shared<GaussianCloud>(opt);
+    return c;
+}
+void spl_cloud_destroy(spl_cloud* c) { delete c; }
+
+int spl_cloud_import_ply(spl_cloud* c, const char* path)
+{
+    if (!c || !path) return set_error(SPL_ERR_ARG, "null argument");
+    if (!c->gc->ImportPly(path)) return set_error(SPL_ERR_IO, c->gc->GetError());
+    return SPL_OK;
+}
+int spl_cloud_export_ply(const spl_cloud* c, const char* path)
+{
+    if (!c || !path) return set_error(SPL_ERR_ARG, "null argument");
+    if (!c->gc->ExportPly(path)) return set_error(SPL_ERR_IO, c->gc->GetError());
+    return SPL_OK;
+}
+int spl_cloud_init_debug_cloud(spl_cloud* c)
+{
+    if (!c) return set_error(SPL_ERR_ARG, "null argument");
+    c->gc->InitDebugCloud();
+    return SPL_OK;
+}
+int spl_cloud_prune_splats(spl_cloud* c, const float origin[3], uint32_t count)
+{
+    if (!c || !origin) return set_error(SPL_ERR_ARG, "null argument");
+    c->gc->PruneSplats(splat::vec3{origin[0], origin[1], origin[2]}, count);
+    return SPL_OK;
+}
+int spl_cloud_set_raw(spl_cloud* c, const void* aos, size_t n, size_t stride, int has_full_sh)
+{
+    if (!c || (!aos && n)) return set_error(SPL_ERR_ARG, "null argument");
+    if (!c->gc->SetRawData(aos, n, stride, has_full_sh != 0)) return set_error(SPL_ERR_ARG, c->gc->GetError());
+    return SPL_OK;
+}
+size_t spl_cloud_num_gaussians(const spl_cloud* c) { return c ? c->gc->GetNumGaussians() : 0; }
+size_t spl_cloud_stride(const spl_cloud* c) { return c ? c->gc->GetStride() : 0; }
+size_t spl_cloud_total_size(const spl_cloud* c) { return c ? c->gc->GetTotalSize() : 0; }
+void* spl_cloud_raw_data(spl_cloud* c) { return c ? c->gc->GetRawDataPtr() : nullptr; }
+int spl_cloud_has_full_sh(const spl_cloud* c) { return c && c->gc->HasFullSH(); }
+int spl_cloud_attrib(const spl_cloud* c, int id, int* type, size_t* size, size_t* offset)
+{
+    if (!c || id < 0 || id >= SPL_ATTR_COUNT) return set_error(SPL_ERR_ARG, "bad attribute id");
+    const GaussianCloud& g = *c->gc;
+    const BinaryAttribute* table[SPL_ATTR_COUNT] = {
+        &g.GetPosWithAlphaAttrib(),
+        &g.GetR_SH0Attrib(), &g.GetR_SH1Attrib(), &g.GetR_SH2Attrib(), &g.GetR_SH3Attrib(),
+        &g.GetG_SH0Attrib(), &g.GetG_SH1Attrib(), &g.GetG_SH2Attrib(), &g.GetG_SH3Attrib(),
+        &g.GetB_SH0Attrib(), &g.GetB_SH1Attrib(), &g.GetB_SH2Attrib(), &g.GetB_SH3Attrib(),
+        &g.GetCov3_Col0Attrib(), &g.GetCov3_Col1Attrib(), &g.GetCov3_Col2Attrib()};
+    const BinaryAttribute& a = *table[id];
+    if (type) *type = (int)a.type;
+    if (size) *size = a.size;
+    if (offset) *offset = a.offset;
+    return SPL_OK;
+}
+
+// ------------------------------------------------------------------ renderer
+spl_renderer* spl_renderer_create(void) { return new (std::nothrow) spl_renderer; }
+void spl_renderer_destroy(spl_renderer* h) { delete h; }
+
+int spl_renderer_configure(spl_renderer* h, int device, int fb_format, void* cuda_stream)
+{
+    if (!h || (fb_format != SPL_FB_FP32 && fb_format != SPL_FB_FP16)) return set_error(SPL_ERR_ARG, "bad argument");
+    return from_renderer(h, h->r.Configure(device, (SplatRenderer::FrameBuffer)fb_format, cuda_stream));
+}
+int spl_renderer_init(spl_renderer* h, const spl_cloud* c, int srgb, int use_rgc)
+{
+    if (!h || !c) return set_error(SPL_ERR_ARG, "null argument");
+    return from_renderer(h, h->r.Init(c->gc, srgb != 0, use_rgc != 0));
+}
+int spl_renderer_init_device_aos(spl_renderer* h, const void* device_aos, size_t n, size_t stride, int has_full_sh, int srgb)
+{
+    if (!h || (!device_aos && n)) return set_error(SPL_ERR_ARG, "null argument");
+    return from_renderer(h, h->r.InitFromDevice(device_aos, n, stride, has_full_sh != 0, srgb != 0));
+}
+int spl_renderer_sort(spl_renderer* h, const float cam[16], const float proj[16], const float vp[4], const float nf[2])
+{
+    if (!h || !cam || !proj || !vp || !nf) return set_error(SPL_ERR_ARG, "null argument");
+    h->r.Sort(splat::mat4::from(cam), splat::mat4::from(proj), splat::vec4{vp[0], vp[1], vp[2], vp[3]}, splat::vec2{nf[0], nf[1]});
+    return from_renderer(h, h->r.LastStatus() == 0);
+}
+int spl_renderer_render(spl_renderer* h, const float cam[16], const float proj[16], const float vp[4], const float nf[2])
+{
+    if (!h || !cam || !proj || !vp || !nf) return set_error(SPL_ERR_ARG, "null argument");
+    h->r.Render(splat::mat4::from(cam), splat::mat4::from(proj), splat::vec4{vp[0], vp[1], vp[2], vp[3]}, splat::vec2{nf[0], nf[1]});
+    return from_renderer(h, h->r.LastStatus() == 0);
+}
+int spl_renderer_framebuffer(spl_renderer* h, void** device_ptr, int* w, int* hgt, size_t* pitch, int* fmt)
+{
+    if (!h) return set_error(SPL_ERR_ARG, "null argument");
+    SplatRenderer::FrameBuffer f;
+    if (!h->r.GetFramebuffer(device_ptr, w, hgt, pitch, &f)) return set_error(SPL_ERR_ARG, "no frame rendered yet");
+    if (fmt) *fmt = (int)f;
+    return SPL_OK;
+}
+int spl_renderer_read_framebuffer_async(spl_renderer* h, void* host, size_t bytes)
+{
+    if (!h || !host) return set_error(SPL_ERR_ARG, "null argument");
+    return from_renderer(h, h->r.ReadFramebufferAsync(host, bytes));
+}
+int spl_renderer_read_framebuffer(spl_renderer* h, void* host, size_t bytes)
+{
+    if (!h || !host) return set_error(SPL_ERR_ARG, "null argument");
+    return from_renderer(h, h->r.ReadFramebuffer(host, bytes));
+}
+int spl_renderer_synchronize(spl_renderer* h)
+{
+    if (!h) return set_error(SPL_ERR_ARG, "null argument");
+    return from_renderer(h, h->r.Synchronize());
+}
+int spl_renderer_stats(spl_renderer* h, spl_stats* out)
+{
+    if (!h || !out) return set_error(SPL_ERR_ARG, "null argument");
+    return from_renderer(h, h->r.GetStats(out));
+}
+int spl_renderer_reserve(spl_renderer* h, uint64_t cap)
+{
+    if (!h) return set_error(SPL_ERR_ARG, "null argument");
+    return from_renderer(h, h->r.Reserve(cap));
+}
+int spl_renderer_set_option(spl_renderer* h, int option, double value)
+{
+    if (!h) return set_error(SPL_ERR_ARG, "null argument");
+    return from_renderer(h, h->r.SetOption(option, value));
+}
+int spl_renderer_tap(spl_renderer* h, int what, void* host, size_t bytes)
+{
+    if (!h || !host) return set_error(SPL_ERR_ARG, "null argument");
+    return from_renderer(h, h->r.Tap(what, host, bytes));
+}
+
+}  // extern "C"
+
+// ------------------------------------------------------------------ stand-alone sorter
+struct spl_sorter
+{
+    int device = 0;
+    int numSMs = 148;
+    uint64_t capacity = 0;
+    void* control = nullptr;  // n | tickets | histograms
+    uint32_t* status = nullptr;
+};
+
+namespace
+{
+constexpr size_t kSorterControlBytes = 256 + splat::kMaxSortPasses * splat::kRadixSize * sizeof(uint32_t);
+#define SORTER_TRY(expr)                                                                                   \
+    do                                                                                                     \
+    {                                                                                                      \
+        cudaError_t e__ = (expr);                                                                          \
+        if (e__ != cudaSuccess) return set_error(SPL_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e__)); \
+    } while (0)
+}  // namespace
+
+extern "C" {
+
+spl_sorter* spl_sorter_create(int device, uint64_t capacity)
+{
+    if (cudaSetDevice(device) != cudaSuccess) { set_error(SPL_ERR_CUDA, "cudaSetDevice failed (no CPU fallback exists)"); cudaGetLastError(); return nullptr; }
+    spl_sorter* s = new (std::nothrow) spl_sorter;
+    if (!s) return nullptr;
+    s->device = device;
+    s->capacity = capacity < (uint64_t)splat::kSortTileKeys ? splat::kSortTileKeys : capacity;
+    cudaDeviceProp prop{};
+    if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) s->numSMs = prop.multiProcessorCount;
+    if (cudaMalloc(&s->control, kSorterControlBytes) != cudaSuccess ||
+        cudaMalloc(&s->status, splat::sort_status_bytes(s->capacity, splat::kMaxSortPasses)) != cudaSuccess)
+    {
+        set_error(SPL_ERR_ALLOC, "cudaMalloc failed");
+        cudaFree(s->control);
+        cudaFree(s->status);
+        delete s;
+        return nullptr;
+    }
+    return s;
+}
+void spl_sorter_destroy(spl_sorter* s)
+{
+    if (!s) return;
+    cudaSetDevice(s->device);
+    cudaFree(s->control);
+    cudaFree(s->status);
+    delete s;
+}
+
+int spl_sorter_sort(spl_sorter* s, void* d_keys_in, void* d_vals_in, void* d_keys_out, void* d_vals_out, uint64_t n, int begin_bit, int end_bit,
+                    void* cuda_stream)
+{
+    if (!s || !d_keys_in || !d_vals_in || !d_keys_out || !d_vals_out) return set_error(SPL_ERR_ARG, "null argument");
+    if (n > s->capacity || n > splat::kMaxInstances) return set_error(SPL_ERR_ARG, "n exceeds sorter capacity");
+    if (begin_bit < 0 || end_bit > 64 || end_bit <= begin_bit) return set_error(SPL_ERR_ARG, "bad bit range");
+    SORTER_TRY(cudaSetDevice(s->device));
+    cudaStream_t stream = static_cast<cudaStream_t>(cuda_stream);
+    const int passes = (end_bit - begin_bit + splat::kRadixBits - 1) / splat::kRadixBits;
+    SORTER_TRY(cudaMemsetAsync(s->control, 0, kSorterControlBytes, stream));
+    const uint32_t n32 = (uint32_t)n;
+    SORTER_TRY(cudaMemcpyAsync(s->control, &n32, sizeof n32, cudaMemcpyHostToDevice, stream));
+    uint32_t* ctl = static_cast<uint32_t*>(s->control);
+    splat::SortWorkspace ws{ctl + 64, s->status, ctl + 8, s->capacity};
+    auto* kin = static_cast<unsigned long long*>(d_keys_in);
+    auto* kout = static_cast<unsigned long long*>(d_keys_out);
+    auto* vin = static_cast<uint32_t*>(d_vals_in);
+    auto* vout = static_cast<uint32_t*>(d_vals_out);
+    SORTER_TRY(splat::launch_radix_sort(kin, vin, kout, vout, ctl, s->capacity, begin_bit, end_bit, ws, s->numSMs, stream, nullptr));
+    if ((passes & 1) == 0)
+    {
+        // an even number of passes ends in the input buffers
+        SORTER_TRY(cudaMemcpyAsync(kout, kin, n * 8, cudaMemcpyDeviceToDevice, stream));
+        SORTER_TRY(cudaMemcpyAsync(vout, vin, n * 4, cudaMemcpyDeviceToDevice, stream));
+    }
+    return SPL_OK;
+}
+
+int spl_sort_pairs_host(const uint64_t* keys, const uint32_t* vals, uint64_t n, int begin_bit, int end_bit, uint64_t* keys_out, uint32_t* vals_out)
+{
+    if ((!keys || !vals || !keys_out || !vals_out) && n) return set_error(SPL_ERR_ARG, "null argument");
+    if (n == 0) return SPL_OK;
+    spl_sorter* s = spl_sorter_create(0, n);
+    if (!s) return SPL_ERR_CUDA;
+    const uint64_t padded = n + splat::kSortTileKeys;
+    void *dk0 = nullptr, *dk1 = nullptr, *dv0 = nullptr, *dv1 = nullptr;
+    int rc = SPL_OK;
+    auto run = [&]() -> int {
+        SORTER_TRY(cudaMalloc(&dk0, padded * 8));
+        SORTER_TRY(cudaMalloc(&dk1, padded * 8));
+        SORTER_TRY(cudaMalloc(&dv0, padded * 4));
+        SORTER_TRY(cudaMalloc(&dv1, padded * 4));
+        SORTER_TRY(cudaMemset(dk0, 0, padded * 8));
+        SORTER_TRY(cudaMemset(dk1, 0, padded * 8));
+        SORTER_TRY(cudaMemset(dv0, 0, padded * 4));
+        SORTER_TRY(cudaMemset(dv1, 0, padded * 4));
+        SORTER_TRY(cudaMemcpy(dk0, keys, n * 8, cudaMemcpyHostToDevice));
+        SORTER_TRY(cudaMemcpy(dv0, vals, n * 4, cudaMemcpyHostToDevice));
+        if (int r = spl_sorter_sort(s, dk0, dv0, dk1, dv1, n, begin_bit, end_bit, nullptr)) return r;
+        SORTER_TRY(cudaDeviceSynchronize());
+        SORTER_TRY(cudaMemcpy(keys_out, dk1, n * 8, cudaMemcpyDeviceToHost));
+        SORTER_TRY(cudaMemcpy(vals_out, dv1, n * 4, cudaMemcpyDeviceToHost));
+        return SPL_OK;
+    };
+    rc = run();
+    cudaFree(dk0); cudaFree(dk1); cudaFree(dv0); cudaFree(dv1);
+    spl_sorter_destroy(s);
+    return rc;
+}
+
+void* spl_host_alloc(size_t bytes)
+{
+    void* p = nullptr;
+    if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess)
+    {
+        set_error(SPL_ERR_ALLOC, "cudaHostAlloc failed");
+        cudaGetLastError();
+        return nullptr;
+    }
+    return p;
+}
+void spl_host_free(void* p)
+{
+    if (p) cudaFreeHost(p);
+}
+
+}  // extern "C"

@@ -1,0 +1,45 @@
+// kernels.h -- host-callable launchers of the sm_100a kernels (internal to libsplat_b200.so).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstddef>
+#include <cstdint>
+
+#include "device_common.cuh"
+
+namespace splat
+{
+
+// ---- pack.cu
+size_t packed_cloud_bytes(uint32_t n, int shMode);
+cudaError_t detect_sh_mode(const void* deviceAos, uint32_t n, uint32_t strideBytes, bool hasFullSH, unsigned int* dFlagScratch,
+                           cudaStream_t stream, int* shModeOut);
+cudaError_t pack_cloud(const void* deviceAos, uint32_t n, uint32_t strideBytes, int shMode, void* planes, PackedCloud* out, cudaStream_t stream);
+
+// ---- project.cu
+uint32_t project_num_blocks(uint32_t n);
+cudaError_t launch_project(const PackedCloud& cloud, const FrameConstants& fc, ProjRecord* rec, unsigned long long* keys, uint32_t* vals,
+                           FrameCounters* ctr, unsigned long long* scanState, uint32_t capacity, cudaStream_t stream);
+
+// ---- radix_sort.cu : device-wide LSD radix sort of (u64 key, u32 value) pairs, 8-bit digits, onesweep style
+struct SortWorkspace
+{
+    uint32_t* histograms;  // [kMaxSortPasses][256] global digit counts
+    uint32_t* status;      // [passes][tiles][256] decoupled look-back words
+    uint32_t* tickets;     // [kMaxSortPasses] dynamic tile ids
+    uint64_t capacity;     // keys the status array was sized for
+};
+size_t sort_status_bytes(uint64_t capacity, int passes);
+// keys/vals ping-pong between (A) and (B); passes = ceil((endBit-beginBit)/8); the sorted result is in A when
+// `passes` is even, else in B.
+// nDevice points at the element count in device memory (no host round trip).
+cudaError_t launch_radix_sort(unsigned long long* keysA, uint32_t* valsA, unsigned long long* keysB, uint32_t* valsB,
+                              const uint32_t* nDevice, uint64_t capacity, int beginBit, int endBit, const SortWorkspace& ws,
+                              int numSMs, cudaStream_t stream, int* launches);
+
+// ---- composite.cu
+cudaError_t launch_tile_ranges(const unsigned long long* sortedKeys, const uint32_t* nDevice, uint64_t capacity, uint2* ranges,
+                               uint32_t numTiles, int numSMs, cudaStream_t stream);
+cudaError_t launch_composite(const uint2* ranges, const uint32_t* sortedVals, const ProjRecord* rec, void* framebuffer, int fbFormat,
+                             int width, int height, int tilesX, int tilesY, float earlyOutT, cudaStream_t stream);
+
+}  // namespace splat

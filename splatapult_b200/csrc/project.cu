@@ -1,0 +1,372 @@
+// project.cu -- P: cull + project + SH radiance + 2D conic + (tile|depth) key emission, one fused pass.
+//
+// Replaces, in ONE kernel over the gaussians in storage order (fully coalesced, no index indirection):
+//   K1 shader/presort_compute.glsl:31-57   frustum cull, depth key (the reference appends through a global
+//                                          atomic and then stalls on a counter read-back, splatrenderer.cpp:195-204)
+//   K5 shader/splat_vert.glsl:153-222      view transform, Jacobian, Sigma' = JW Sigma JW^T, +0.3 low-pass,
+//                                          screen centre, SH radiance (:51-127)
+//   K6 shader/splat_geom.glsl:22-54        2x2 inverse, guard-band cull.  The 3.5-sigma quad (:56-104) becomes
+//                                          a conservative tile rectangle.
+// and emits one u64 key (tile << 32 | depthKey) + u32 gaussian id per touched 16x16 tile.  Key slots are
+// assigned by a single-pass decoupled look-back scan over the per-gaussian tile counts, so emission order is
+// the gaussian index order (deterministic; the reference's compaction order is not) and the
+// instance count D never leaves the device.
+//
+// This translation unit is compiled with -fmad=false: every a*b+c below is two IEEE roundings in source
+// order, divisions and square roots are IEEE (nvcc defaults -prec-div/-prec-sqrt=true, -ftz=false), so the
+// projected records equal oracle/splat_oracle.c:project_one() bit for bit.  The kernel is HBM-bound; the
+// extra unfused flops are free.
+#include "device_common.cuh"
+#include "kernels.h"
+
+namespace splat
+{
+
+constexpr int kProjThreads = 256;
+constexpr unsigned long long kScanAggregate = 1ull << 62;
+constexpr unsigned long long kScanPrefix = 2ull << 62;
+constexpr unsigned long long kScanValueMask = (1ull << 62) - 1;
+
+#define M4(m, c, r) ((m)[(c) * 4 + (r)])
+#define M3(m, c, r) ((m)[(c) * 3 + (r)])
+
+__device__ __forceinline__ void xform_point(const float* m, float x, float y, float z, float* o)
+{
+#pragma unroll
+    for (int r = 0; r < 4; r++) o[r] = ((M4(m, 0, r) * x + M4(m, 1, r) * y) + M4(m, 2, r) * z) + M4(m, 3, r);
+}
+__device__ __forceinline__ void xform_vec4(const float* m, const float* v, float* o)
+{
+#pragma unroll
+    for (int r = 0; r < 4; r++) o[r] = ((M4(m, 0, r) * v[0] + M4(m, 1, r) * v[1]) + M4(m, 2, r) * v[2]) + M4(m, 3, r) * v[3];
+}
+__device__ __forceinline__ void mat3_mul(const float* a, const float* b, float* out)
+{
+    float t[9];
+#pragma unroll
+    for (int c = 0; c < 3; c++)
+#pragma unroll
+        for (int r = 0; r < 3; r++) t[c * 3 + r] = (M3(a, 0, r) * M3(b, c, 0) + M3(a, 1, r) * M3(b, c, 1)) + M3(a, 2, r) * M3(b, c, 2);
+#pragma unroll
+    for (int k = 0; k < 9; k++) out[k] = t[k];
+}
+
+__device__ __forceinline__ float srgb_to_linear(float s)
+{
+    if (s <= 0.04045f) return s / 12.92f;
+    return powf((s + 0.055f) / 1.055f, 2.4f);
+}
+
+// splat_vert.glsl:51-127; sh planes hold vec4 blocks {r,g,b}_sh{0..3}
+template <int SH_MODE>
+__device__ __forceinline__ void radiance(const PackedCloud& cloud, uint32_t i, float vx, float vy, float vz, float* rgb)
+{
+    float b[16];
+    const float vx2 = vx * vx, vy2 = vy * vy, vz2 = vz * vz;
+    b[0] = 0.28209479177387814f;
+    const float k1 = 0.4886025119029199f;
+    b[1] = -k1 * vy;
+    b[2] = k1 * vz;
+    b[3] = -k1 * vx;
+    if (SH_MODE == 3)
+    {
+        const float k2 = 1.0925484305920792f, k3 = 0.31539156525252005f, k4 = 0.5462742152960396f;
+        b[4] = k2 * vy * vx;
+        b[5] = -k2 * vy * vz;
+        b[6] = k3 * (3.0f * vz2 - 1.0f);
+        b[7] = -k2 * vx * vz;
+        b[8] = k4 * (vx2 - vy2);
+        const float k5 = 0.5900435899266435f, k6 = 2.8906114426405543f, k7 = 0.4570457994644658f;
+        const float k8 = 0.37317633259011546f, k9 = 1.4453057213202771f;
+        b[9] = -k5 * vy * (3.0f * vx2 - vy2);
+        b[10] = k6 * vy * vx * vz;
+        b[11] = -k7 * vy * (5.0f * vz2 - 1.0f);
+        b[12] = k8 * vz * (5.0f * vz2 - 3.0f);
+        b[13] = -k7 * vx * (5.0f * vz2 - 1.0f);
+        b[14] = k9 * vz * (vx2 - vy2);
+        b[15] = -k5 * vx * (vx2 - 3.0f * vy2);
+    }
+#pragma unroll
+    for (int c = 0; c < 3; c++)
+    {
+        float acc;
+        if (SH_MODE == 0)
+        {
+            // degree-1 slots are exact zeros in this layout: b[k]*0 contributes +-0 and cannot change acc
+            acc = b[0] * __ldg(cloud.dc[c] + i);
+        }
+        else if (SH_MODE == 1)
+        {
+            const float4 s0 = __ldg(cloud.sh[c] + i);
+            acc = b[0] * s0.x;
+            acc = acc + b[1] * s0.y;
+            acc = acc + b[2] * s0.z;
+            acc = acc + b[3] * s0.w;
+        }
+        else
+        {
+            float4 s = __ldg(cloud.sh[4 * c] + i);
+            acc = b[0] * s.x;
+            acc = acc + b[1] * s.y;
+            acc = acc + b[2] * s.z;
+            acc = acc + b[3] * s.w;
+#pragma unroll
+            for (int j = 1; j < 4; j++)
+            {
+                s = __ldg(cloud.sh[4 * c + j] + i);
+                acc = acc + b[4 * j + 0] * s.x;
+                acc = acc + b[4 * j + 1] * s.y;
+                acc = acc + b[4 * j + 2] * s.z;
+                acc = acc + b[4 * j + 3] * s.w;
+            }
+        }
+        rgb[c] = 0.5f + acc;
+    }
+}
+
+template <int SH_MODE>
+__global__ void __launch_bounds__(kProjThreads)
+k_project(const PackedCloud cloud, const __grid_constant__ FrameConstants fc, ProjRecord* __restrict__ rec,
+          unsigned long long* __restrict__ keys, uint32_t* __restrict__ vals, FrameCounters* __restrict__ ctr,
+          unsigned long long* __restrict__ scanState, uint32_t capacity)
+{
+    __shared__ uint32_t sBlockId;
+    __shared__ uint32_t sWarpTotal[kProjThreads / 32];
+    __shared__ unsigned long long sBlockBase;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) sBlockId = atomicAdd(&ctr->projectTicket, 1u);  // dynamic id: predecessors are resident or done
+    __syncthreads();
+    const uint32_t vbid = sBlockId;
+    const uint32_t i = vbid * kProjThreads + tid;
+    const bool inRange = i < cloud.n;
+
+    uint32_t count = 0, rect = 0, refKey = 0;
+    bool visible = false;
+
+    if (inRange)
+    {
+        const float4 pa = __ldg(cloud.posAlpha + i);
+        const float x = pa.x, y = pa.y, z = pa.z, alpha = pa.w;
+
+        // ---- K1 presort_compute.glsl:42-56
+        float p[4];
+        xform_point(fc.mvp, x, y, z, p);
+        const float depth = p[3];
+        const float xx = p[0] / depth, yy = p[1] / depth;
+        const float CLIP = 1.5f;
+        bool keep = (depth > 0.0f && xx < CLIP && xx > -CLIP && yy < CLIP && yy > -CLIP);
+        keep = keep && (depth < fc.zFar);  // uint() overflow is undefined in GLSL; the quad is far-clipped anyway
+        if (keep)
+        {
+            const float q = (depth / fc.zFar) * 4294967296.0f;
+            refKey = 0xFFFFFFFFu - __float2uint_rz(q);
+        }
+        // ---- K5/K6 transforms + guard band (splat_vert.glsl:157,200-201 ; splat_geom.glsl:46-54)
+        float t[4], p4[4];
+        xform_point(fc.view, x, y, z, t);
+        xform_vec4(fc.proj, t, p4);
+        const float ndcx = p4[0] / p4[3], ndcy = p4[1] / p4[3], ndcz = p4[2] / p4[3];
+        if (ndcz < 0.25f || ndcx > 2.0f || ndcx < -2.0f || ndcy > 2.0f || ndcy < -2.0f) keep = false;
+
+        float4 q2 = make_float4(0.0f, alpha, __uint_as_float(refKey), __uint_as_float(0u));
+        if (keep)
+        {
+            const float WIDTH = fc.W, HEIGHT = fc.H, Z_NEAR = fc.zNear, Z_FAR = fc.zFar;
+            const float SX = M4(fc.proj, 0, 0), SY = M4(fc.proj, 1, 1), WZ = M4(fc.proj, 3, 2);
+            const float tzSq = t[2] * t[2];
+            const float jsx = -(SX * WIDTH) / (2.0f * t[2]);
+            const float jsy = -(SY * HEIGHT) / (2.0f * t[2]);
+            const float jtx = (SX * t[0] * WIDTH) / (2.0f * tzSq);
+            const float jty = (SY * t[1] * HEIGHT) / (2.0f * tzSq);
+            const float jtz = ((Z_FAR - Z_NEAR) * WZ) / (2.0f * tzSq);
+            float J[9] = {jsx, 0.0f, 0.0f, 0.0f, jsy, 0.0f, jtx, jty, jtz};  // columns (splat_vert.glsl:179-181)
+            float Wm[9];
+#pragma unroll
+            for (int c = 0; c < 3; c++)
+#pragma unroll
+                for (int r = 0; r < 3; r++) M3(Wm, c, r) = M4(fc.view, c, r);
+            const float4 ca = __ldg(cloud.covA + i), cb = __ldg(cloud.covB + i);
+            float V[9] = {ca.x, ca.y, ca.z, ca.w, cb.x, cb.y, cb.z, cb.w, __ldg(cloud.covC + i)};
+            float JW[9], JWt[9], Vp[9];
+            mat3_mul(J, Wm, JW);
+#pragma unroll
+            for (int c = 0; c < 3; c++)
+#pragma unroll
+                for (int r = 0; r < 3; r++) M3(JWt, c, r) = M3(JW, r, c);
+            mat3_mul(JW, V, Vp);
+            mat3_mul(Vp, JWt, Vp);
+            const float m00 = M3(Vp, 0, 0) + 0.3f, m01 = M3(Vp, 0, 1), m10 = M3(Vp, 1, 0), m11 = M3(Vp, 1, 1) + 0.3f;
+            const float det = m00 * m11 - m01 * m10;
+            if ((det > 0.0f) && (det <= 3.4028234e38f))  // degenerate covariance: skipped (oracle does the same)
+            {
+                visible = true;
+                const float i00 = m11 / det, i01 = -m01 / det, i10 = -m10 / det, i11 = m00 / det;
+                const float gx = p4[0] / p4[3], gy = p4[1] / p4[3];
+                const float px = 0.5f * (WIDTH + (gx * WIDTH) + (2.0f * 0.0f));
+                const float py = 0.5f * (HEIGHT + (gy * HEIGHT) + (2.0f * 0.0f));
+                const float dx = x - fc.eye[0], dy = y - fc.eye[1], dz = z - fc.eye[2];
+                const float len = sqrtf((dx * dx + dy * dy) + dz * dz);
+                float rgb[3];
+                radiance<SH_MODE>(cloud, i, dx / len, dy / len, dz / len, rgb);
+                if (fc.srgb)
+                {
+#pragma unroll
+                    for (int c = 0; c < 3; c++) rgb[c] = srgb_to_linear(rgb[c]);
+                }
+                float4* out = reinterpret_cast<float4*>(rec + i);
+                out[0] = make_float4(px, py, i00, i01);
+                out[1] = make_float4(i10, i11, rgb[0], rgb[1]);
+                q2 = make_float4(rgb[2], alpha, __uint_as_float(refKey), __uint_as_float(1u));
+
+                // ---- tile rectangle (not in the reference: stands in for the 3.5-sigma quad + rasteriser).
+                // A pixel contributes iff alpha*exp(-Q/2) > 1/256 (splat_frag.glsl:38-41)  <=>  Q < 2 ln(256 alpha);
+                // the axis-aligned extent of {Q <= r2} is sqrt(r2 * Sigma_xx), sqrt(r2 * Sigma_yy).  Inflated so
+                // rounding can never drop a contributing pixel centre.
+                const float r2 = 2.0f * logf(256.0f * alpha);
+                if (r2 > 0.0f)
+                {
+                    const float ex = sqrtf(r2 * m00) * 1.001f + 0.01f;
+                    const float ey = sqrtf(r2 * m11) * 1.001f + 0.01f;
+                    // pixel centres x+0.5 in [px-ex, px+ex]
+                    const float fx0 = fmaxf(ceilf(px - ex - 0.5f), 0.0f), fx1 = fminf(floorf(px + ex - 0.5f), (float)(fc.width - 1));
+                    const float fy0 = fmaxf(ceilf(py - ey - 0.5f), 0.0f), fy1 = fminf(floorf(py + ey - 0.5f), (float)(fc.height - 1));
+                    if (fx1 >= fx0 && fy1 >= fy0)  // false for NaN too
+                    {
+                        const uint32_t tx0 = (uint32_t)fx0 >> kTileShift, tx1 = (uint32_t)fx1 >> kTileShift;
+                        const uint32_t ty0 = (uint32_t)fy0 >> kTileShift, ty1 = (uint32_t)fy1 >> kTileShift;
+                        const uint32_t w = tx1 - tx0 + 1, h = ty1 - ty0 + 1;
+                        count = w * h;
+                        rect = tx0 | (ty0 << 10) | ((w - 1) << 20);
+                    }
+                }
+            }
+        }
+        reinterpret_cast<float4*>(rec + i)[2] = q2;  // {b, alpha, key, visible}: always written
+    }
+
+    // ---- block-wide exclusive scan of the tile counts
+    uint32_t incl = count;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1)
+    {
+        const uint32_t v = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += v;
+    }
+    if (lane == 31) sWarpTotal[warp] = incl;
+    const uint32_t nVisibleWarp = __popc(__ballot_sync(0xffffffffu, visible));
+    __syncthreads();
+    uint32_t warpBase = 0, blockTotal = 0;
+#pragma unroll
+    for (int w = 0; w < kProjThreads / 32; w++)
+    {
+        const uint32_t t = sWarpTotal[w];
+        if (w < warp) warpBase += t;
+        blockTotal += t;
+    }
+
+    // ---- decoupled look-back over block aggregates (warp 0)
+    if (warp == 0)
+    {
+        unsigned long long excl = 0;
+        if (lane == 0) st_relaxed_u64(scanState + vbid, (vbid == 0 ? kScanPrefix : kScanAggregate) | blockTotal);
+        if (vbid > 0)
+        {
+            int base = (int)vbid - 1;
+            for (;;)
+            {
+                const int j = base - lane;
+                unsigned long long s = kScanPrefix;  // virtual predecessor of block 0: prefix 0
+                if (j >= 0)
+                {
+                    do { s = ld_relaxed_u64(scanState + j); } while ((s >> 62) == 0);
+                }
+                const bool isPrefix = (s >> 62) == 2;
+                const uint32_t pmask = __ballot_sync(0xffffffffu, isPrefix);
+                const int firstP = pmask ? (__ffs(pmask) - 1) : 32;
+                unsigned long long v = (lane <= firstP) ? (s & kScanValueMask) : 0ull;
+#pragma unroll
+                for (int d = 16; d; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+                excl += v;
+                if (pmask) break;
+                base -= 32;
+            }
+            if (lane == 0) st_relaxed_u64(scanState + vbid, kScanPrefix | (excl + blockTotal));
+        }
+        if (lane == 0)
+        {
+            sBlockBase = excl;
+            if (vbid == gridDim.x - 1) ctr->totalInstances = excl + blockTotal;
+        }
+    }
+    if (lane == 0 && nVisibleWarp) atomicAdd(&ctr->visible, nVisibleWarp);
+    __syncthreads();
+
+    // ---- warp-cooperative, coalesced key emission
+    const unsigned long long gOff64 = sBlockBase + warpBase + (incl - count);
+    const bool fits = gOff64 + count <= (unsigned long long)capacity;
+    const uint32_t cntE = fits ? count : 0u;
+    if (!fits) atomicOr(&ctr->overflow, 1u);
+    const uint32_t gOff = fits ? (uint32_t)gOff64 : 0u;
+
+    uint32_t inclE = cntE;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1)
+    {
+        const uint32_t v = __shfl_up_sync(0xffffffffu, inclE, d);
+        if (lane >= d) inclE += v;
+    }
+    const uint32_t wexE = inclE - cntE;
+    const uint32_t T = __shfl_sync(0xffffffffu, inclE, 31);
+
+    uint32_t usedEnd = cntE ? gOff + cntE : 0u;
+#pragma unroll
+    for (int d = 16; d; d >>= 1) usedEnd = max(usedEnd, __shfl_xor_sync(0xffffffffu, usedEnd, d));
+    if (lane == 0 && usedEnd) atomicMax(&ctr->usedInstances, usedEnd);
+
+    const uint32_t tilesX = (uint32_t)fc.tilesX;
+    for (uint32_t j0 = 0; j0 < T; j0 += 32)
+    {
+        const uint32_t j = j0 + lane;
+        int owner = 0;
+#pragma unroll
+        for (int s = 16; s; s >>= 1)
+        {
+            const int cand = owner + s;
+            const uint32_t v = __shfl_sync(0xffffffffu, wexE, cand);
+            if (v <= j) owner = cand;
+        }
+        const uint32_t oBase = __shfl_sync(0xffffffffu, wexE, owner);
+        const uint32_t oOff = __shfl_sync(0xffffffffu, gOff, owner);
+        const uint32_t oRect = __shfl_sync(0xffffffffu, rect, owner);
+        const uint32_t oKey = __shfl_sync(0xffffffffu, refKey, owner);
+        const uint32_t oId = __shfl_sync(0xffffffffu, i, owner);
+        if (j < T)
+        {
+            const uint32_t k = j - oBase;
+            const uint32_t w = (oRect >> 20) + 1, x0 = oRect & 1023u, y0 = (oRect >> 10) & 1023u;
+            const uint32_t row = k / w, col = k - row * w;
+            const uint32_t tile = (y0 + row) * tilesX + (x0 + col);
+            keys[oOff + k] = ((unsigned long long)tile << 32) | oKey;
+            vals[oOff + k] = oId;
+        }
+    }
+}
+
+cudaError_t launch_project(const PackedCloud& cloud, const FrameConstants& fc, ProjRecord* rec, unsigned long long* keys, uint32_t* vals,
+                           FrameCounters* ctr, unsigned long long* scanState, uint32_t capacity, cudaStream_t stream)
+{
+    const uint32_t blocks = project_num_blocks(cloud.n);
+    if (blocks == 0) return cudaSuccess;
+    switch (cloud.shMode)
+    {
+    case 0: k_project<0><<<blocks, kProjThreads, 0, stream>>>(cloud, fc, rec, keys, vals, ctr, scanState, capacity); break;
+    case 1: k_project<1><<<blocks, kProjThreads, 0, stream>>>(cloud, fc, rec, keys, vals, ctr, scanState, capacity); break;
+    default: k_project<3><<<blocks, kProjThreads, 0, stream>>>(cloud, fc, rec, keys, vals, ctr, scanState, capacity); break;
+    }
+    return cudaGetLastError();
+}
+
+uint32_t project_num_blocks(uint32_t n) { return (n + kProjThreads - 1) / kProjThreads; }
+
+}  // namespace splat

@@ -1,0 +1,482 @@
+// renderer.cu -- SplatRenderer: owns the device buffers and enqueues the frame (P -> S1 -> S2 x passes -> ranges -> C).
+//
+// Call protocol and argument meaning follow the reference (src/splatrenderer.h:23-67, src/splatrenderer.cpp:50-343):
+//   Init   : src/splatrenderer.cpp:50-151   (upload the cloud once; no reference to host data afterwards)
+//   Sort   : src/splatrenderer.cpp:153-312  (pre-sort + radix sort; here also projection/SH and tile ranges)
+//   Render : src/splatrenderer.cpp:315-343  (the draw; here the per-tile compositor into an explicit target)
+// Unlike the reference there is no host synchronisation on the frame path and no GL state: the render target,
+// its clear colour (0,0,0,1) and the "over" blend (src/app.cpp:144-164) are part of Render itself.
+#include "splatapult_b200/splatrenderer.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+
+#include "kernels.h"
+#include "splat_b200.h"
+
+namespace splat
+{
+
+#define CU_TRY(expr)                                                                                 \
+    do                                                                                               \
+    {                                                                                                \
+        cudaError_t e__ = (expr);                                                                    \
+        if (e__ != cudaSuccess) return fail(SPL_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e__)); \
+    } while (0)
+
+struct RendererImpl
+{
+    // configuration
+    int device = 0;
+    int fbFormat = SPL_FB_FP32;
+    cudaStream_t stream = nullptr;
+    bool ownStream = false;
+    int numSMs = 148;
+    double earlyOutT = 1e-4;
+    bool profile = false;
+    double instancesPerGaussian = 16.0;
+
+    // cloud
+    bool initialized = false;
+    bool srgb = false;
+    uint32_t n = 0;
+    void* dPlanes = nullptr;
+    PackedCloud cloud{};
+    ProjRecord* dRec = nullptr;
+
+    // per-frame buffers
+    uint64_t capacity = 0;
+    unsigned long long *dKeysA = nullptr, *dKeysB = nullptr;
+    uint32_t *dValsA = nullptr, *dValsB = nullptr;
+    void* dControl = nullptr;
+    size_t controlBytes = 0;
+    FrameCounters* dCtr = nullptr;
+    uint32_t* dHist = nullptr;
+    unsigned long long* dScan = nullptr;
+    uint32_t* dStatus = nullptr;
+    uint2* dRanges = nullptr;
+    uint32_t rangesTiles = 0;
+    void* dFb = nullptr;
+    size_t fbBytes = 0;
+    int fbW = 0, fbH = 0;
+
+    // last frame
+    bool haveSort = false, haveRender = false;
+    FrameConstants fc{};
+    float lastArgs[16 + 16 + 4 + 2] = {};
+    int sortPasses = 0, sortBits = 0;
+    uint32_t launches = 0;
+    cudaEvent_t ev[6] = {};
+    bool evCreated = false;
+
+    int status = 0;
+    std::string error;
+
+    int fail(int code, const std::string& msg)
+    {
+        status = code;
+        error = msg;
+        return code;
+    }
+    int ok()
+    {
+        status = 0;
+        return 0;
+    }
+
+    ~RendererImpl() { release(); }
+
+    void freeFrameBuffers()
+    {
+        cudaFree(dKeysA); cudaFree(dKeysB); cudaFree(dValsA); cudaFree(dValsB); cudaFree(dStatus);
+        dKeysA = dKeysB = nullptr; dValsA = dValsB = nullptr; dStatus = nullptr;
+        capacity = 0;
+    }
+    void release()
+    {
+        if (!initialized && !stream && !dFb) return;
+        cudaSetDevice(device);
+        if (stream) cudaStreamSynchronize(stream);
+        freeFrameBuffers();
+        cudaFree(dPlanes); cudaFree(dRec); cudaFree(dControl); cudaFree(dRanges); cudaFree(dFb);
+        dPlanes = nullptr; dRec = nullptr; dControl = nullptr; dRanges = nullptr; dFb = nullptr;
+        if (evCreated)
+            for (auto& e : ev) cudaEventDestroy(e);
+        evCreated = false;
+        if (ownStream && stream) cudaStreamDestroy(stream);
+        stream = nullptr;
+        ownStream = false;
+        initialized = false;
+    }
+
+    int begin()
+    {
+        cudaError_t e = cudaSetDevice(device);
+        if (e != cudaSuccess) return fail(SPL_ERR_CUDA, std::string("cudaSetDevice: ") + cudaGetErrorString(e) + " (no CPU fallback exists)");
+        if (!stream)
+        {
+            CU_TRY(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+            ownStream = true;
+        }
+        return 0;
+    }
+
+    int reserve(uint64_t want)
+    {
+        want = std::min<uint64_t>(std::max<uint64_t>(want, kSortTileKeys), kMaxInstances);
+        if (want <= capacity) return ok();
+        CU_TRY(cudaStreamSynchronize(stream));
+        freeFrameBuffers();
+        const uint64_t padded = want + kSortTileKeys;  // bulk copies may read up to a tile past the last key
+        CU_TRY(cudaMalloc(&dKeysA, padded * 8));
+        CU_TRY(cudaMalloc(&dKeysB, padded * 8));
+        CU_TRY(cudaMalloc(&dValsA, padded * 4));
+        CU_TRY(cudaMalloc(&dValsB, padded * 4));
+        CU_TRY(cudaMalloc(&dStatus, sort_status_bytes(want, kMaxSortPasses)));
+        // the padding is read (never used) by the last tile's bulk copy: keep it defined
+        CU_TRY(cudaMemsetAsync(dKeysA, 0, padded * 8, stream));
+        CU_TRY(cudaMemsetAsync(dKeysB, 0, padded * 8, stream));
+        CU_TRY(cudaMemsetAsync(dValsA, 0, padded * 4, stream));
+        CU_TRY(cudaMemsetAsync(dValsB, 0, padded * 4, stream));
+        capacity = want;
+        return ok();
+    }
+
+    int initFromDevice(const void* dAos, size_t count, size_t stride, bool fullSH, bool srgbIn)
+    {
+        if (int rc = begin()) return rc;
+        if (stride != 100 && stride != 244) return fail(SPL_ERR_ARG, "stride must be 100 (base) or 244 (full SH)");
+        if (fullSH && stride != 244) return fail(SPL_ERR_ARG, "full SH needs stride 244");
+        if (count >= (1ull << 31)) return fail(SPL_ERR_ARG, "too many gaussians");
+        cudaDeviceProp prop{};
+        CU_TRY(cudaGetDeviceProperties(&prop, device));
+        numSMs = prop.multiProcessorCount;
+        if (prop.major < 10) return fail(SPL_ERR_CUDA, "libsplat_b200 is built for sm_100a only (found sm_" + std::to_string(prop.major * 10 + prop.minor) + ")");
+
+        // drop any previous cloud
+        CU_TRY(cudaStreamSynchronize(stream));
+        cudaFree(dPlanes); cudaFree(dRec); cudaFree(dControl);
+        dPlanes = nullptr; dRec = nullptr; dControl = nullptr;
+
+        n = (uint32_t)count;
+        srgb = srgbIn;
+        // control block: counters | histograms | projection scan state
+        const size_t scanBytes = (size_t)std::max<uint32_t>(project_num_blocks(n), 1) * sizeof(unsigned long long);
+        controlBytes = 256 + kMaxSortPasses * kRadixSize * sizeof(uint32_t) + scanBytes;
+        CU_TRY(cudaMalloc(&dControl, controlBytes));
+        dCtr = reinterpret_cast<FrameCounters*>(dControl);
+        dHist = reinterpret_cast<uint32_t*>(static_cast<uint8_t*>(dControl) + 256);
+        dScan = reinterpret_cast<unsigned long long*>(static_cast<uint8_t*>(dControl) + 256 + kMaxSortPasses * kRadixSize * sizeof(uint32_t));
+        CU_TRY(cudaMemsetAsync(dControl, 0, controlBytes, stream));
+
+        int shMode = 0;
+        CU_TRY(detect_sh_mode(dAos, n, (uint32_t)stride, fullSH, reinterpret_cast<unsigned int*>(dControl), stream, &shMode));
+        CU_TRY(cudaMemsetAsync(dControl, 0, 256, stream));
+        CU_TRY(cudaMalloc(&dPlanes, packed_cloud_bytes(n, shMode)));
+        CU_TRY(pack_cloud(dAos, n, (uint32_t)stride, shMode, dPlanes, &cloud, stream));
+        CU_TRY(cudaMalloc(&dRec, std::max<size_t>(n, 1) * sizeof(ProjRecord)));
+        CU_TRY(cudaMemsetAsync(dRec, 0, std::max<size_t>(n, 1) * sizeof(ProjRecord), stream));
+        if (int rc = reserve((uint64_t)std::ceil(std::max(1.0, instancesPerGaussian) * std::max<uint32_t>(n, 1)))) return rc;
+        CU_TRY(cudaStreamSynchronize(stream));
+        initialized = true;
+        haveSort = haveRender = false;
+        return ok();
+    }
+
+    int initFromHost(const GaussianCloud& gc, bool srgbIn)
+    {
+        if (int rc = begin()) return rc;
+        const size_t bytes = gc.GetTotalSize();
+        void* dAos = nullptr;
+        CU_TRY(cudaMalloc(&dAos, std::max<size_t>(bytes, 16)));
+        cudaError_t e = cudaMemcpyAsync(dAos, gc.GetRawDataPtr(), bytes, cudaMemcpyHostToDevice, stream);
+        int rc = 0;
+        if (e != cudaSuccess) rc = fail(SPL_ERR_CUDA, std::string("H2D cloud copy: ") + cudaGetErrorString(e));
+        else rc = initFromDevice(dAos, gc.GetNumGaussians(), gc.GetStride(), gc.HasFullSH() && gc.GetStride() == 244, srgbIn);
+        cudaStreamSynchronize(stream);
+        cudaFree(dAos);
+        return rc;
+    }
+
+    static bool sameArgs(const float* a, const float* cam, const float* proj, const float* vp, const float* nf)
+    {
+        return !std::memcmp(a, cam, 64) && !std::memcmp(a + 16, proj, 64) && !std::memcmp(a + 32, vp, 16) && !std::memcmp(a + 36, nf, 8);
+    }
+
+    int sort(const float* cam, const float* proj, const float* vp, const float* nf)
+    {
+        if (int rc = begin()) return rc;
+        if (!initialized) return fail(SPL_ERR_ARG, "Sort before Init");
+        if (vp[0] != 0.0f || vp[1] != 0.0f) return fail(SPL_ERR_ARG, "viewport origin must be (0,0) (the reference assumes it, SURVEY q6)");
+        const int W = (int)vp[2], H = (int)vp[3];
+        if (W <= 0 || H <= 0 || (float)W != vp[2] || (float)H != vp[3]) return fail(SPL_ERR_ARG, "viewport width/height must be positive integers");
+        const int tilesX = (W + kTileSize - 1) / kTileSize, tilesY = (H + kTileSize - 1) / kTileSize;
+        if (tilesX > 1024 || tilesY > 1024) return fail(SPL_ERR_ARG, "viewport larger than 16384 pixels");
+
+        // frame constants, computed as the reference's CPU side does (float, glm operation order)
+        const mat4 camera = mat4::from(cam), projM = mat4::from(proj);
+        const mat4 view = inverse(camera);          // src/splatrenderer.cpp:161,327
+        const mat4 mvp = mul(projM, view);          // src/splatrenderer.cpp:175
+        std::memcpy(fc.view, view.m, 64);
+        std::memcpy(fc.mvp, mvp.m, 64);
+        std::memcpy(fc.proj, projM.m, 64);
+        fc.eye[0] = camera.at(3, 0); fc.eye[1] = camera.at(3, 1); fc.eye[2] = camera.at(3, 2);  // :328
+        fc.W = vp[2]; fc.H = vp[3]; fc.zNear = nf[0]; fc.zFar = nf[1];
+        fc.width = W; fc.height = H; fc.tilesX = tilesX; fc.tilesY = tilesY;
+        fc.srgb = srgb ? 1 : 0;
+        std::memcpy(lastArgs, cam, 64); std::memcpy(lastArgs + 16, proj, 64); std::memcpy(lastArgs + 32, vp, 16); std::memcpy(lastArgs + 36, nf, 8);
+
+        const uint32_t numTiles = (uint32_t)tilesX * tilesY;
+        if (numTiles > rangesTiles)
+        {
+            CU_TRY(cudaStreamSynchronize(stream));
+            cudaFree(dRanges);
+            dRanges = nullptr;
+            CU_TRY(cudaMalloc(&dRanges, (size_t)numTiles * sizeof(uint2)));
+            rangesTiles = numTiles;
+        }
+        int tileBits = 0;
+        while ((1u << tileBits) < numTiles) tileBits++;
+        sortBits = kDepthBits + tileBits;
+        sortPasses = (sortBits + kRadixBits - 1) / kRadixBits;
+
+        if (profile && !evCreated)
+        {
+            for (auto& e : ev) CU_TRY(cudaEventCreate(&e));
+            evCreated = true;
+        }
+        launches = 0;
+        int sortLaunches = 0;
+        if (profile) CU_TRY(cudaEventRecord(ev[0], stream));
+        CU_TRY(cudaMemsetAsync(dControl, 0, controlBytes, stream));
+        CU_TRY(launch_project(cloud, fc, dRec, dKeysA, dValsA, dCtr, dScan, (uint32_t)capacity, stream));
+        launches += n ? 1 : 0;
+        if (profile) CU_TRY(cudaEventRecord(ev[1], stream));
+        SortWorkspace ws{dHist, dStatus, dCtr->sortTickets, capacity};
+        CU_TRY(launch_radix_sort(dKeysA, dValsA, dKeysB, dValsB, &dCtr->usedInstances, capacity, 0, sortBits, ws, numSMs, stream, &sortLaunches));
+        launches += sortLaunches;
+        if (profile) CU_TRY(cudaEventRecord(ev[2], stream));
+        CU_TRY(launch_tile_ranges(sortedKeys(), &dCtr->usedInstances, capacity, dRanges, numTiles, numSMs, stream));
+        launches += 1;
+        if (profile) CU_TRY(cudaEventRecord(ev[3], stream));
+        haveSort = true;
+        return ok();
+    }
+
+    const unsigned long long* sortedKeys() const { return (sortPasses & 1) ? dKeysB : dKeysA; }
+    const uint32_t* sortedVals() const { return (sortPasses & 1) ? dValsB : dValsA; }
+
+    int render(const float* cam, const float* proj, const float* vp, const float* nf)
+    {
+        if (int rc = begin()) return rc;
+        if (!initialized) return fail(SPL_ERR_ARG, "Render before Init");
+        // The reference's Render re-projects with its own arguments in the order of the last Sort (the VR path
+        // sorts for eye 0 only, src/app.cpp:603-607).  Here projection lives in Sort; a Render whose arguments
+        // differ from the last Sort re-runs Sort so the image is always that of the arguments given.
+        if (!haveSort || !sameArgs(lastArgs, cam, proj, vp, nf))
+            if (int rc = sort(cam, proj, vp, nf)) return rc;
+        const size_t need = (size_t)fc.width * fc.height * (fbFormat == SPL_FB_FP16 ? 8 : 16);
+        if (need > fbBytes)
+        {
+            CU_TRY(cudaStreamSynchronize(stream));
+            cudaFree(dFb);
+            dFb = nullptr;
+            CU_TRY(cudaMalloc(&dFb, need));
+            fbBytes = need;
+        }
+        fbW = fc.width; fbH = fc.height;
+        if (profile) CU_TRY(cudaEventRecord(ev[4], stream));
+        CU_TRY(launch_composite(dRanges, sortedVals(), dRec, dFb, fbFormat, fc.width, fc.height, fc.tilesX, fc.tilesY, (float)earlyOutT, stream));
+        launches += 1;
+        if (profile) CU_TRY(cudaEventRecord(ev[5], stream));
+        haveRender = true;
+        return ok();
+    }
+
+    int readCounters(FrameCounters* out)
+    {
+        CU_TRY(cudaMemcpyAsync(out, dCtr, sizeof(FrameCounters), cudaMemcpyDeviceToHost, stream));
+        CU_TRY(cudaStreamSynchronize(stream));
+        return 0;
+    }
+
+    int readFramebuffer(void* host, size_t bytes, bool wait)
+    {
+        if (int rc = begin()) return rc;
+        if (!haveRender) return fail(SPL_ERR_ARG, "no frame rendered yet");
+        const size_t need = (size_t)fbW * fbH * (fbFormat == SPL_FB_FP16 ? 8 : 16);
+        if (bytes < need) return fail(SPL_ERR_ARG, "host buffer too small for the framebuffer");
+        if (wait)
+        {
+            // a frame that ran out of key capacity is incomplete: grow and redo it once
+            FrameCounters c{};
+            if (int rc = readCounters(&c)) return rc;
+            if (c.overflow)
+            {
+                if (c.totalInstances > kMaxInstances) return fail(SPL_ERR_OVERFLOW, "frame needs more than 2^30 tile instances");
+                if (int rc = reserve(c.totalInstances + c.totalInstances / 4)) return rc;
+                float a[38];
+                std::memcpy(a, lastArgs, sizeof a);
+                haveSort = false;
+                if (int rc = render(a, a + 16, a + 32, a + 36)) return rc;
+            }
+        }
+        CU_TRY(cudaMemcpyAsync(host, dFb, need, cudaMemcpyDeviceToHost, stream));
+        if (wait) CU_TRY(cudaStreamSynchronize(stream));
+        return ok();
+    }
+
+    int stats(spl_stats* out)
+    {
+        if (int rc = begin()) return rc;
+        if (!initialized) return fail(SPL_ERR_ARG, "stats before Init");
+        std::memset(out, 0, sizeof *out);
+        FrameCounters c{};
+        if (int rc = readCounters(&c)) return rc;
+        out->num_gaussians = n;
+        out->num_visible = c.visible;
+        out->num_instances = c.totalInstances;
+        out->instance_capacity = capacity;
+        out->overflow = c.overflow;
+        out->tiles_x = fc.tilesX; out->tiles_y = fc.tilesY; out->tile_size = kTileSize;
+        out->sort_passes = sortPasses; out->sort_bits = sortBits;
+        out->sh_mode = cloud.shMode;
+        out->kernel_launches = launches;
+        if (profile && evCreated && haveSort)
+        {
+            float ms = 0;
+            // stage_ms: project(+memset), sort (histogram + passes), ranges, composite, total
+            if (cudaEventElapsedTime(&ms, ev[0], ev[1]) == cudaSuccess) out->stage_ms[0] = ms;
+            if (cudaEventElapsedTime(&ms, ev[1], ev[2]) == cudaSuccess) out->stage_ms[2] = ms;
+            if (cudaEventElapsedTime(&ms, ev[2], ev[3]) == cudaSuccess) out->stage_ms[3] = ms;
+            if (haveRender)
+            {
+                if (cudaEventElapsedTime(&ms, ev[4], ev[5]) == cudaSuccess) out->stage_ms[4] = ms;
+                if (cudaEventElapsedTime(&ms, ev[0], ev[5]) == cudaSuccess) out->stage_ms[7] = ms;
+            }
+        }
+        return ok();
+    }
+
+    int tap(int what, void* host, size_t bytes)
+    {
+        if (int rc = begin()) return rc;
+        if (!haveSort) return fail(SPL_ERR_ARG, "tap before Sort");
+        FrameCounters c{};
+        if (int rc = readCounters(&c)) return rc;
+        const void* src = nullptr;
+        size_t have = 0;
+        switch (what)
+        {
+        case SPL_TAP_RECORDS: src = dRec; have = (size_t)n * sizeof(ProjRecord); break;
+        case SPL_TAP_KEYS: src = sortedKeys(); have = (size_t)c.usedInstances * 8; break;
+        case SPL_TAP_VALS: src = sortedVals(); have = (size_t)c.usedInstances * 4; break;
+        case SPL_TAP_TILE_RANGES: src = dRanges; have = (size_t)fc.tilesX * fc.tilesY * sizeof(uint2); break;
+        default: return fail(SPL_ERR_ARG, "unknown tap");
+        }
+        if (bytes < have) return fail(SPL_ERR_ARG, "tap buffer too small");
+        if (have) CU_TRY(cudaMemcpyAsync(host, src, have, cudaMemcpyDeviceToHost, stream));
+        CU_TRY(cudaStreamSynchronize(stream));
+        return ok();
+    }
+};
+
+}  // namespace splat
+
+using splat::RendererImpl;
+
+SplatRenderer::SplatRenderer() : impl(new RendererImpl) {}
+SplatRenderer::~SplatRenderer() = default;
+
+#define FORWARD(call)            \
+    do                           \
+    {                            \
+        status = (call);         \
+        error = impl->error;     \
+        return status == 0;      \
+    } while (0)
+
+bool SplatRenderer::Configure(int device, FrameBuffer format, void* cudaStream)
+{
+    if (impl->initialized) { status = SPL_ERR_ARG; error = "Configure must precede Init"; return false; }
+    impl->device = device;
+    impl->fbFormat = (int)format;
+    if (impl->ownStream && impl->stream) { cudaSetDevice(impl->device); cudaStreamDestroy(impl->stream); impl->ownStream = false; }
+    impl->stream = static_cast<cudaStream_t>(cudaStream);
+    status = 0;
+    return true;
+}
+
+bool SplatRenderer::Init(std::shared_ptr<GaussianCloud> gaussianCloud, bool isFramebufferSRGBEnabledIn, bool useRgcSortOverrideIn)
+{
+    (void)useRgcSortOverrideIn;  // both reference sorters give the same stable order; one CUDA sort replaces both
+    if (!gaussianCloud) { status = SPL_ERR_ARG; error = "null cloud"; return false; }
+    FORWARD(impl->initFromHost(*gaussianCloud, isFramebufferSRGBEnabledIn));
+}
+
+bool SplatRenderer::InitFromDevice(const void* deviceAos, size_t numGaussians, size_t stride, bool hasFullSH, bool isFramebufferSRGBEnabledIn)
+{
+    FORWARD(impl->initFromDevice(deviceAos, numGaussians, stride, hasFullSH, isFramebufferSRGBEnabledIn));
+}
+
+void SplatRenderer::Sort(const splat::mat4& cameraMat, const splat::mat4& projMat, const splat::vec4& viewport, const splat::vec2& nearFar)
+{
+    status = impl->sort(cameraMat.m, projMat.m, &viewport.x, &nearFar.x);
+    error = impl->error;
+    if (status) std::fprintf(stderr, "SplatRenderer::Sort: %s\n", error.c_str());  // the reference logs and carries on
+}
+
+void SplatRenderer::Render(const splat::mat4& cameraMat, const splat::mat4& projMat, const splat::vec4& viewport, const splat::vec2& nearFar)
+{
+    status = impl->render(cameraMat.m, projMat.m, &viewport.x, &nearFar.x);
+    error = impl->error;
+    if (status) std::fprintf(stderr, "SplatRenderer::Render: %s\n", error.c_str());
+}
+
+bool SplatRenderer::GetFramebuffer(void** devicePtr, int* width, int* height, size_t* rowPitchBytes, FrameBuffer* format) const
+{
+    if (!impl->haveRender) return false;
+    if (devicePtr) *devicePtr = impl->dFb;
+    if (width) *width = impl->fbW;
+    if (height) *height = impl->fbH;
+    if (rowPitchBytes) *rowPitchBytes = (size_t)impl->fbW * (impl->fbFormat == SPL_FB_FP16 ? 8 : 16);
+    if (format) *format = (FrameBuffer)impl->fbFormat;
+    return true;
+}
+
+bool SplatRenderer::ReadFramebufferAsync(void* host, size_t bytes) { FORWARD(impl->readFramebuffer(host, bytes, false)); }
+bool SplatRenderer::ReadFramebuffer(void* host, size_t bytes) { FORWARD(impl->readFramebuffer(host, bytes, true)); }
+
+bool SplatRenderer::Synchronize()
+{
+    if (int rc = impl->begin()) { status = rc; error = impl->error; return false; }
+    cudaError_t e = cudaStreamSynchronize(impl->stream);
+    if (e != cudaSuccess) { status = impl->fail(SPL_ERR_CUDA, std::string("cudaStreamSynchronize: ") + cudaGetErrorString(e)); error = impl->error; return false; }
+    status = 0;
+    return true;
+}
+
+bool SplatRenderer::GetStats(spl_stats* out) { FORWARD(impl->stats(out)); }
+
+bool SplatRenderer::Reserve(uint64_t instanceCapacity)
+{
+    if (int rc = impl->begin()) { status = rc; error = impl->error; return false; }
+    FORWARD(impl->reserve(instanceCapacity));
+}
+
+bool SplatRenderer::SetOption(int option, double value)
+{
+    switch (option)
+    {
+    case SPL_OPT_EARLY_OUT_T: impl->earlyOutT = value; break;
+    case SPL_OPT_PROFILE: impl->profile = value != 0.0; break;
+    case SPL_OPT_INSTANCES_PER_GAUSSIAN: impl->instancesPerGaussian = value; break;
+    default: status = SPL_ERR_ARG; error = "unknown option"; return false;
+    }
+    status = 0;
+    return true;
+}
+
+bool SplatRenderer::Tap(int what, void* host, size_t bytes) { FORWARD(impl->tap(what, host, bytes)); }
