@@ -1,0 +1,418 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the splat hot path (BASELINE.json: Msplats/s at 1920x1080).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload NAME]
+
+A "step" is one frame: SplatRenderer::Sort + SplatRenderer::Render of the whole cloud from one camera into a
+cleared 1920x1080 float framebuffer.  Workloads:
+    1m_deg0       BASELINE configs[1]: 1M synthetic gaussians, SH degree 0, fp32 target      (default)
+    1m_deg3       BASELINE configs[2]: 1M synthetic gaussians, full SH (48 coeffs), fp32 target
+    6m_deg3_fp16  BASELINE configs[3]: 6M gaussians, full SH, fp16 target
+`value` = gaussians in the cloud x frames x ranks / device time (inputs resident in HBM, L2 flushed between
+frames); `e2e` = the same through the C ABI with host camera matrices in and the framebuffer copied to pinned
+host memory every frame.  N > 1 (torchrun, one rank per GPU): views shard one per GPU, the cloud is
+NCCL-broadcast once at start-up (not timed), no per-frame collective ("scaling": "weak").
+--impl reference times the reference path's CPU stand-in (the oracle: the reference's GLSL cannot run here,
+there is no OpenGL) on the host cores, rank 0 only.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+WORKLOADS = {
+    #  name            n          deg seed      half  cam_z  fb      baseline config
+    "1m_deg0": dict(n=1_000_000, deg=0, seed=20240916, half=4.0, cam_z=10.0, fp16=False, cfg="configs[1]"),
+    "1m_deg3": dict(n=1_000_000, deg=3, seed=20240916, half=4.0, cam_z=10.0, fp16=False, cfg="configs[2]"),
+    "6m_deg3_fp16": dict(n=6_000_000, deg=3, seed=20240917, half=7.3, cam_z=18.0, fp16=True, cfg="configs[3]"),
+}
+WIDTH, HEIGHT = 1920, 1080
+SCENE_DIR = os.environ.get("SPLAT_SCENE_DIR", "/tmp/splat_b200_scenes")
+
+
+def scene_path(name: str) -> str:
+    from splatapult_b200 import scenes
+
+    w = WORKLOADS[name]
+    os.makedirs(SCENE_DIR, exist_ok=True)
+    path = os.path.join(SCENE_DIR, f"{name}_{w['n']}.ply")
+    if not os.path.exists(path):
+        scenes.write_synthetic_ply(path, w["n"], w["deg"], seed=w["seed"], half_extent=w["half"])
+    return path
+
+
+def camera_for_rank(name: str, rank: int, world: int) -> np.ndarray:
+    """rank 0 renders the BASELINE camera (translate(0,0,z)); other ranks their own view on a ring of the same radius."""
+    from splatapult_b200 import scenes
+
+    z = WORKLOADS[name]["cam_z"]
+    if rank == 0:
+        return scenes.translate(0, 0, z)
+    ang = 2.0 * math.pi * rank / max(world, 1)
+    return scenes.look_at_camera((z * math.sin(ang), 0.0, z * math.cos(ang)), (0.0, 0.0, 0.0))
+
+
+def measured_peak_gbs():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs, copy burst)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.rows = []
+        self.proc = None
+        self.gpu = gpu_index
+        self.thread = None
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.gpu)],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def __exit__(self, *a):
+        if self.proc:
+            time.sleep(0.15)
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self) -> dict:
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                mx.append(float(r[2]))
+            except Exception:
+                continue
+            for name, col in (("hw_slowdown", 5), ("hw_thermal_slowdown", 6), ("sw_thermal_slowdown", 7), ("sw_power_cap", 8)):
+                if len(r) > col and r[col].lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def algorithmic_bytes(n, v, d, deg_mode, passes, tiles, pixels, fp16):
+    """information bytes, not padded strides."""
+    rec = {0: 52, 1: 88, 3: 232}[deg_mode]
+    b_p = 16 * n + (rec - 16) * v + 48 * v + 12 * d
+    b_hist = 8 * d
+    b_pass = 24 * d
+    b_ranges = 8 * d + 8 * tiles
+    b_c = 4 * d + 48 * v + 8 * tiles + pixels * (8 if fp16 else 16)
+    return {"project": b_p, "sort_histogram": b_hist, "sort_pass": b_pass, "tile_ranges": b_ranges, "composite": b_c,
+            "frame": b_p + b_hist + passes * b_pass + b_ranges + b_c}
+
+
+def run_ours(args, rank, local_rank, world):
+    import torch
+    import torch.distributed as dist
+
+    import splatapult_b200 as sp
+    from splatapult_b200 import api
+
+    w = WORKLOADS[args.workload]
+    if sp.device_count() < 1:
+        raise RuntimeError("bench.py needs a CUDA device: splatapult_b200 has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    stream = torch.cuda.Stream(device=dev)
+    vp, nf = [0, 0, WIDTH, HEIGHT], [sp.Z_NEAR, sp.Z_FAR]
+    proj = sp.perspective(sp.FOVY, WIDTH / HEIGHT)
+    cam = camera_for_rank(args.workload, rank, world)
+
+    # ---- load through the same .ply path a splatapult user has; broadcast once for N > 1
+    t0 = time.perf_counter()
+    broadcast_ms = None
+    r = sp.SplatRenderer(device=local_rank, fb_format=api.FB_FP16 if w["fp16"] else api.FB_FP32, cuda_stream=stream.cuda_stream)
+    if world == 1:
+        gc = sp.GaussianCloud(import_full_sh=True, export_full_sh=True)
+        if not gc.ImportPly(scene_path(args.workload)):
+            raise RuntimeError(gc.LastError())
+        n_gauss, full = gc.GetNumGaussians(), gc.HasFullSH()
+        if not r.Init(gc, False, False):
+            raise RuntimeError(r.last_error)
+        del gc
+    else:
+        meta = [None]
+        if rank == 0:
+            gc = sp.GaussianCloud(import_full_sh=True, export_full_sh=True)
+            if not gc.ImportPly(scene_path(args.workload)):
+                raise RuntimeError(gc.LastError())
+            host = gc.GetRawData()
+            meta = [(gc.GetNumGaussians(), gc.GetStride(), gc.HasFullSH())]
+        dist.broadcast_object_list(meta, src=0)
+        n_gauss, stride, full = meta[0]
+        buf = torch.empty((n_gauss, stride // 4), dtype=torch.float32, device=dev)
+        if rank == 0:
+            buf.copy_(torch.from_numpy(host))
+        torch.cuda.synchronize()
+        dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        dist.broadcast(buf, src=0)  # NCCL over NVLink/NVSwitch, once at start-up
+        e1.record()
+        torch.cuda.synchronize()
+        broadcast_ms = e0.elapsed_time(e1)
+        r.InitFromDevice(buf.data_ptr(), n_gauss, stride, full)
+        del buf
+    load_s = time.perf_counter() - t0
+
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+
+    def frame():
+        r.Sort(cam, proj, vp, nf)
+        r.Render(cam, proj, vp, nf)
+
+    with torch.cuda.stream(stream):
+        for _ in range(max(args.warmup, 3)):
+            flush.zero_()
+            frame()
+        stream.synchronize()
+        st = r.GetStats()
+        if st.overflow:  # grow once, outside the timed region
+            r.Reserve(int(st.num_instances * 1.25))
+            frame()
+            stream.synchronize()
+            st = r.GetStats()
+            assert not st.overflow
+
+        # ---- timed: K frames, device time per frame (CUDA events on the launching stream), L2 flushed in between
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        with ClockSampler(local_rank) as clocks:
+            wall0 = time.perf_counter()
+            for a, b in ev:
+                flush.zero_()
+                a.record(stream)
+                frame()
+                b.record(stream)
+            stream.synchronize()
+            wall = time.perf_counter() - wall0
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        step_ms = [a.elapsed_time(b) for a, b in ev]
+        total_ms = float(sum(step_ms))
+
+        # ---- end to end through the C ABI: host matrices in, framebuffer out to pinned host memory, every frame
+        fb_bytes = WIDTH * HEIGHT * (8 if w["fp16"] else 16)
+        pinned = [sp.host_alloc(fb_bytes), sp.host_alloc(fb_bytes)]
+        for i in range(2):
+            frame()
+            r.ReadFramebufferAsync(pinned[i].ptr, fb_bytes)
+        stream.synchronize()
+        if world > 1:
+            dist.barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(stream)
+        for i in range(args.steps):
+            frame()
+            r.ReadFramebufferAsync(pinned[i & 1].ptr, fb_bytes)
+        b.record(stream)
+        stream.synchronize()
+        e2e_ms = a.elapsed_time(b)
+        checksum = float(pinned[(args.steps - 1) & 1].array(np.float16 if w["fp16"] else np.float32, (HEIGHT, WIDTH, 4))[..., :3].mean())
+
+        # ---- per-stage profile (separate, untimed pass): events between the kernels
+        r.SetOption(api.OPT_PROFILE, 1)
+        stages = np.zeros(8)
+        reps = 10
+        for _ in range(reps):
+            flush.zero_()
+            frame()
+            stream.synchronize()
+            stages += np.array(r.GetStats().stage_ms)
+        stages /= reps
+        r.SetOption(api.OPT_PROFILE, 0)
+        st = r.GetStats()
+
+    if world > 1:
+        t = torch.tensor([total_ms, e2e_ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms, e2e_ms = float(t[0]), float(t[1])
+
+    if rank != 0:
+        return None
+
+    n, v, d = int(st.num_gaussians), int(st.num_visible), int(st.num_instances)
+    tiles = int(st.tiles_x * st.tiles_y)
+    ab = algorithmic_bytes(n, v, d, int(st.sh_mode), int(st.sort_passes), tiles, WIDTH * HEIGHT, w["fp16"])
+    peak, peak_src = measured_peak_gbs()
+    stage = {"project": stages[0], "sort_histogram": stages[1], "sort_passes_total": stages[2], "tile_ranges": stages[3],
+             "composite": stages[4], "frame": stages[7]}
+    pass_ms = stages[2] / max(int(st.sort_passes), 1)
+    cand = {"composite": (stages[4], ab["composite"], stages[4]), "sort_onesweep": (stages[2], ab["sort_pass"], pass_ms),
+            "project": (stages[0], ab["project"], stages[0])}
+    dom = max(cand, key=lambda k: cand[k][0])
+    dom_total, dom_bytes, dom_launch_ms = cand[dom]
+    achieved = dom_bytes / (dom_launch_ms * 1e-3) / 1e9 if dom_launch_ms > 0 else 0.0
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            traffic = json.load(f).get(args.workload, {}).get(dom)
+    except Exception:
+        pass
+
+    secs = total_ms * 1e-3
+    value = n * args.steps * world / secs / 1e6
+    out = {
+        "metric": "Msplats/sec at 1920x1080", "value": value, "unit": "Msplats/s", "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{args.workload}: {w['cfg']} of BASELINE.json -- {n} synthetic gaussians (seed {w['seed']}), SH degree {w['deg']}, "
+                               f"{WIDTH}x{HEIGHT}, {'fp16' if w['fp16'] else 'fp32'} framebuffer, one view per GPU",
+                   "l2": "flushed between timed frames (256 MiB memset, untimed); e2e loop: per-frame working set > L2",
+                   "tile": 16, "early_out_T": 1e-4, "sort_bits": int(st.sort_bits), "sort_passes": int(st.sort_passes),
+                   "visible": v, "tile_instances": d, "parallelism": f"views x{world}"},
+        "frames_per_s": args.steps * world / secs,
+        "sort_gkeys_per_s": (d / ((stages[1] + stages[2]) * 1e-3) / 1e9) if (stages[1] + stages[2]) > 0 else None,
+        "clocks": clocks.summary(),
+        "e2e": {"value": n * args.steps * world / (e2e_ms * 1e-3) / 1e6, "unit": "Msplats/s", "h2d_bytes_per_step": 38 * 4,
+                "d2h_bytes_per_step": fb_bytes, "ms_per_step": e2e_ms / args.steps, "framebuffer_mean": checksum},
+        "gpu_launches": int(st.kernel_launches) * args.steps,
+        "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": dom_bytes,
+                     "launch_ms": dom_launch_ms, "share_of_step": dom_total / stages[7] if stages[7] > 0 else None,
+                     "frame": {"algorithmic_bytes": ab["frame"], "achieved": ab["frame"] / (stages[7] * 1e-3) / 1e9 if stages[7] > 0 else None,
+                               "frac": ab["frame"] / (stages[7] * 1e-3) / 1e9 / peak if stages[7] > 0 else None}},
+        "stage_ms": {k: float(x) for k, x in stage.items()},
+        "stage_gbs": {k: (ab[k] / (stage[k] * 1e-3) / 1e9 if stage[k] > 0 else None) for k in ("project", "sort_histogram", "tile_ranges", "composite")},
+        "wall_s_timed_loop": wall, "load_s": load_s, "broadcast_ms": broadcast_ms,
+    }
+    out["stage_gbs"]["sort_pass"] = ab["sort_pass"] / (pass_ms * 1e-3) / 1e9 if pass_ms > 0 else None
+    if world == 1 and not args.no_cpu_baseline:
+        out["cpu_baseline"] = cpu_baseline(args.workload, steps=2, warmup=1)
+    return out
+
+
+def cpu_baseline(workload: str, steps: int, warmup: int, budget_s: float = 150.0, impl_line: bool = False):
+    """The reference path's CPU stand-in (oracle/splat_oracle.c, "port") on the box's host cores."""
+    from oracle import splat_oracle as O
+    from splatapult_b200 import scenes
+
+    w = WORKLOADS[workload]
+    aos, full = O.import_ply(scene_path(workload), True)
+    cam = scenes.translate(0, 0, w["cam_z"])
+    proj = scenes.perspective(scenes.FOVY, WIDTH / HEIGHT)
+    vp, nf = [0, 0, WIDTH, HEIGHT], [scenes.Z_NEAR, scenes.Z_FAR]
+    cores = O.num_threads()
+    n = len(aos)
+    # first (warm-up) frame sizes the sample so that warmup+steps stay inside the budget
+    t0 = time.perf_counter()
+    O.render(aos, full, cam, proj, vp, nf, fp16=w["fp16"])
+    t_full = time.perf_counter() - t0
+    frac = min(1.0, budget_s / max(t_full * (steps + warmup), 1e-9))
+    m = n if frac >= 1.0 else max(int(n * frac), 1000)
+    sub = aos[:m]
+    for _ in range(max(warmup - 1, 0)):
+        O.render(sub, full, cam, proj, vp, nf, fp16=w["fp16"])
+    times, stage = [], np.zeros(3)
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        _, _, _, ms = O.render(sub, full, cam, proj, vp, nf, fp16=w["fp16"], want_records=True)
+        times.append(time.perf_counter() - t0)
+        stage += np.array(ms)
+    total = float(sum(times))
+    sample = (f"{steps} whole frame(s) of the same workload ({m} of {n} gaussians, 1920x1080) after {warmup} warm-up"
+              if m == n else f"{steps} frame(s) of the first {m} of {n} gaussians (bounded sample), 1920x1080, after {warmup} warm-up")
+    base = {"value": m * steps / total / 1e6, "unit": "Msplats/s", "cores": cores, "kind": "port", "sample": sample,
+            "ms_per_frame": total / steps * 1e3, "stage_ms": {"project": stage[0] / steps, "sort": stage[1] / steps, "composite": stage[2] / steps}}
+    if impl_line:
+        return base, total, m
+    return base
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return None
+    w = WORKLOADS[args.workload]
+    base, total, m = cpu_baseline(args.workload, steps=args.steps, warmup=max(args.warmup, 1), impl_line=True)
+    return {
+        "impl": "reference", "metric": "Msplats/sec at 1920x1080", "value": base["value"], "unit": "Msplats/s", "n_gpus": world,
+        "steps": args.steps, "warmup": max(args.warmup, 1), "ms_per_step": total / args.steps * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{args.workload}: {w['cfg']} of BASELINE.json, {WIDTH}x{HEIGHT}; reference arm = CPU oracle (the reference's GLSL/OpenGL "
+                               "path cannot execute on this box), all host threads, rank 0 only"},
+        "cpu_baseline": base,
+        "e2e": {"value": base["value"], "unit": "Msplats/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="1m_deg0", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    if args.impl == "reference":
+        if args.steps > 5 and "--steps" not in " ".join(sys.argv):
+            args.steps = 3
+        out = run_reference(args, rank, world)
+        if out is not None:
+            print(json.dumps(out), flush=True)
+        return
+
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    if rank == 0:
+        scene_path(args.workload)  # generate before anybody needs it
+    out = run_ours(args, rank, local_rank, world)
+    if out is not None:
+        print(json.dumps(out), flush=True)
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

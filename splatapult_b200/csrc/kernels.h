@@ -36,6 +36,11 @@ cudaError_t launch_radix_sort(unsigned long long* keysA, uint32_t* valsA, unsign
                               const uint32_t* nDevice, uint64_t capacity, int beginBit, int endBit, const SortWorkspace& ws,
                               int numSMs, cudaStream_t stream, int* launches);
 
+cudaError_t launch_sort_histogram(const unsigned long long* keysA, const uint32_t* nDevice, uint64_t capacity, int beginBit, int endBit,
+                                  const SortWorkspace& ws, int numSMs, cudaStream_t stream);
+cudaError_t launch_sort_passes(unsigned long long* keysA, uint32_t* valsA, unsigned long long* keysB, uint32_t* valsB, const uint32_t* nDevice,
+                               uint64_t capacity, int beginBit, int endBit, const SortWorkspace& ws, int numSMs, cudaStream_t stream);
+
 // ---- composite.cu
 cudaError_t launch_tile_ranges(const unsigned long long* sortedKeys, const uint32_t* nDevice, uint64_t capacity, uint2* ranges,
                                uint32_t numTiles, int numSMs, cudaStream_t stream);

@@ -305,17 +305,11 @@ size_t sort_status_bytes(uint64_t capacity, int passes)
     return (size_t)passes * maxTiles * kRadixSize * sizeof(uint32_t);
 }
 
-cudaError_t launch_radix_sort(unsigned long long* keysA, uint32_t* valsA, unsigned long long* keysB, uint32_t* valsB, const uint32_t* nDevice,
-                              uint64_t capacity, int beginBit, int endBit, const SortWorkspace& ws, int numSMs, cudaStream_t stream, int* launches)
+static cudaError_t ensure_sort_attrs(size_t histSmem, size_t sortSmem)
 {
-    const int passes = (endBit - beginBit + kRadixBits - 1) / kRadixBits;
-    if (passes < 1 || passes > kMaxSortPasses) return cudaErrorInvalidValue;
-    const uint32_t maxTiles = (uint32_t)((capacity + kSortTileKeys - 1) / kSortTileKeys + 1);
     static bool attrSet[64] = {};
     int dev = 0;
     cudaGetDevice(&dev);
-    const size_t histSmem = 2 * kSortTileKeys * sizeof(unsigned long long) + (size_t)kMaxSortPasses * kRadixSize * sizeof(uint32_t);
-    const size_t sortSmem = sizeof(SortSmem);
     if (!attrSet[dev & 63])
     {
         cudaError_t e = cudaFuncSetAttribute(k_sort_histogram, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)histSmem);
@@ -324,9 +318,34 @@ cudaError_t launch_radix_sort(unsigned long long* keysA, uint32_t* valsA, unsign
         if (e != cudaSuccess) return e;
         attrSet[dev & 63] = true;
     }
+    return cudaSuccess;
+}
+
+static constexpr size_t kHistSmemBytes = 2 * kSortTileKeys * sizeof(unsigned long long) + (size_t)kMaxSortPasses * kRadixSize * sizeof(uint32_t);
+
+cudaError_t launch_sort_histogram(const unsigned long long* keysA, const uint32_t* nDevice, uint64_t capacity, int beginBit, int endBit,
+                                  const SortWorkspace& ws, int numSMs, cudaStream_t stream)
+{
+    const int passes = (endBit - beginBit + kRadixBits - 1) / kRadixBits;
+    if (passes < 1 || passes > kMaxSortPasses) return cudaErrorInvalidValue;
+    cudaError_t e = ensure_sort_attrs(kHistSmemBytes, sizeof(SortSmem));
+    if (e != cudaSuccess) return e;
+    const uint32_t maxTiles = (uint32_t)((capacity + kSortTileKeys - 1) / kSortTileKeys + 1);
     const uint32_t capTiles = (uint32_t)((capacity + kSortTileKeys - 1) / kSortTileKeys);
     const uint32_t histGrid = max(1u, min((uint32_t)numSMs * 3u, capTiles));
-    k_sort_histogram<<<histGrid, kHistThreads, histSmem, stream>>>(keysA, nDevice, beginBit, endBit, passes, ws.histograms, ws.status, maxTiles);
+    k_sort_histogram<<<histGrid, kHistThreads, kHistSmemBytes, stream>>>(keysA, nDevice, beginBit, endBit, passes, ws.histograms, ws.status, maxTiles);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_sort_passes(unsigned long long* keysA, uint32_t* valsA, unsigned long long* keysB, uint32_t* valsB, const uint32_t* nDevice,
+                               uint64_t capacity, int beginBit, int endBit, const SortWorkspace& ws, int numSMs, cudaStream_t stream)
+{
+    const int passes = (endBit - beginBit + kRadixBits - 1) / kRadixBits;
+    if (passes < 1 || passes > kMaxSortPasses) return cudaErrorInvalidValue;
+    cudaError_t e = ensure_sort_attrs(kHistSmemBytes, sizeof(SortSmem));
+    if (e != cudaSuccess) return e;
+    const uint32_t maxTiles = (uint32_t)((capacity + kSortTileKeys - 1) / kSortTileKeys + 1);
+    const uint32_t capTiles = (uint32_t)((capacity + kSortTileKeys - 1) / kSortTileKeys);
     const uint32_t sortGrid = max(1u, min((uint32_t)numSMs * 3u, capTiles));
     for (int p = 0; p < passes; p++)
     {
@@ -334,12 +353,22 @@ cudaError_t launch_radix_sort(unsigned long long* keysA, uint32_t* valsA, unsign
         const uint32_t* vin = (p & 1) ? valsB : valsA;
         unsigned long long* kout = (p & 1) ? keysA : keysB;
         uint32_t* vout = (p & 1) ? valsA : valsB;
-        k_sort_onesweep<<<sortGrid, kSortThreads, sortSmem, stream>>>(kin, vin, kout, vout, nDevice, beginBit + p * kRadixBits, digit_mask(beginBit + p * kRadixBits, endBit),
-                                                                      ws.histograms + p * kRadixSize,
-                                                                      ws.status + (size_t)p * maxTiles * kRadixSize, ws.tickets + p);
+        const int shift = beginBit + p * kRadixBits;
+        k_sort_onesweep<<<sortGrid, kSortThreads, sizeof(SortSmem), stream>>>(kin, vin, kout, vout, nDevice, shift, digit_mask(shift, endBit),
+                                                                              ws.histograms + p * kRadixSize,
+                                                                              ws.status + (size_t)p * maxTiles * kRadixSize, ws.tickets + p);
     }
-    if (launches) *launches += 1 + passes;
     return cudaGetLastError();
+}
+
+cudaError_t launch_radix_sort(unsigned long long* keysA, uint32_t* valsA, unsigned long long* keysB, uint32_t* valsB, const uint32_t* nDevice,
+                              uint64_t capacity, int beginBit, int endBit, const SortWorkspace& ws, int numSMs, cudaStream_t stream, int* launches)
+{
+    cudaError_t e = launch_sort_histogram(keysA, nDevice, capacity, beginBit, endBit, ws, numSMs, stream);
+    if (e != cudaSuccess) return e;
+    e = launch_sort_passes(keysA, valsA, keysB, valsB, nDevice, capacity, beginBit, endBit, ws, numSMs, stream);
+    if (launches) *launches += 1 + (endBit - beginBit + kRadixBits - 1) / kRadixBits;
+    return e;
 }
 
 }  // namespace splat

@@ -68,7 +68,7 @@ struct RendererImpl
     float lastArgs[16 + 16 + 4 + 2] = {};
     int sortPasses = 0, sortBits = 0;
     uint32_t launches = 0;
-    cudaEvent_t ev[6] = {};
+    cudaEvent_t ev[7] = {};
     bool evCreated = false;
 
     int status = 0;
@@ -255,7 +255,10 @@ struct RendererImpl
         launches += n ? 1 : 0;
         if (profile) CU_TRY(cudaEventRecord(ev[1], stream));
         SortWorkspace ws{dHist, dStatus, dCtr->sortTickets, capacity};
-        CU_TRY(launch_radix_sort(dKeysA, dValsA, dKeysB, dValsB, &dCtr->usedInstances, capacity, 0, sortBits, ws, numSMs, stream, &sortLaunches));
+        CU_TRY(launch_sort_histogram(dKeysA, &dCtr->usedInstances, capacity, 0, sortBits, ws, numSMs, stream));
+        if (profile) CU_TRY(cudaEventRecord(ev[6], stream));
+        CU_TRY(launch_sort_passes(dKeysA, dValsA, dKeysB, dValsB, &dCtr->usedInstances, capacity, 0, sortBits, ws, numSMs, stream));
+        sortLaunches = 1 + sortPasses;
         launches += sortLaunches;
         if (profile) CU_TRY(cudaEventRecord(ev[2], stream));
         CU_TRY(launch_tile_ranges(sortedKeys(), &dCtr->usedInstances, capacity, dRanges, numTiles, numSMs, stream));
@@ -347,9 +350,10 @@ struct RendererImpl
         if (profile && evCreated && haveSort)
         {
             float ms = 0;
-            // stage_ms: project(+memset), sort (histogram + passes), ranges, composite, total
+            // stage_ms: [0] project(+memset) [1] sort histogram [2] sort scatter passes [3] tile ranges [4] composite [7] total
             if (cudaEventElapsedTime(&ms, ev[0], ev[1]) == cudaSuccess) out->stage_ms[0] = ms;
-            if (cudaEventElapsedTime(&ms, ev[1], ev[2]) == cudaSuccess) out->stage_ms[2] = ms;
+            if (cudaEventElapsedTime(&ms, ev[1], ev[6]) == cudaSuccess) out->stage_ms[1] = ms;
+            if (cudaEventElapsedTime(&ms, ev[6], ev[2]) == cudaSuccess) out->stage_ms[2] = ms;
             if (cudaEventElapsedTime(&ms, ev[2], ev[3]) == cudaSuccess) out->stage_ms[3] = ms;
             if (haveRender)
             {
