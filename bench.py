@@ -86,7 +86,7 @@ class ClockSampler:
 
     def __enter__(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.gpu)],
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50", "-i", str(self.gpu)],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -123,14 +123,23 @@ class ClockSampler:
         return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def algorithmic_bytes(n, v, d, deg_mode, passes, tiles, pixels, fp16):
-    """information bytes, not padded strides."""
+def algorithmic_bytes(n, v, d, deg_mode, passes, tiles, pixels, fp16, binned):
+    """information bytes per stage (not padded strides), for the sort path actually run.
+    rec = 16 (pos+alpha) + 24 (symmetric Sigma) + SH {12 | 48 | 192}."""
     rec = {0: 52, 1: 88, 3: 232}[deg_mode]
+    fbb = pixels * (8 if fp16 else 16)
+    if binned:
+        # P: read cloud, write 48 B records + 16 B side records (rect, key, count); per-instance REDs not counted
+        b_p = 16 * n + (rec - 16) * v + 48 * v + 16 * n
+        b_bin = 16 * n + 8 * d + 16 * tiles          # scan + scatter: side records in, (key,id) pairs out
+        b_seg = 16 * d                               # every segment read once and written once
+        b_c = 8 * d + 48 * v + 8 * tiles + fbb       # pairs once, each record once (L2 re-gathers not credited)
+        return {"project": b_p, "bin_scatter": b_bin, "segment_sort": b_seg, "composite": b_c, "frame": b_p + b_bin + b_seg + b_c}
     b_p = 16 * n + (rec - 16) * v + 48 * v + 12 * d
     b_hist = 8 * d
     b_pass = 24 * d
     b_ranges = 8 * d + 8 * tiles
-    b_c = 4 * d + 48 * v + 8 * tiles + pixels * (8 if fp16 else 16)
+    b_c = 4 * d + 48 * v + 8 * tiles + fbb
     return {"project": b_p, "sort_histogram": b_hist, "sort_pass": b_pass, "tile_ranges": b_ranges, "composite": b_c,
             "frame": b_p + b_hist + passes * b_pass + b_ranges + b_c}
 
@@ -189,6 +198,7 @@ def run_ours(args, rank, local_rank, world):
         del buf
     load_s = time.perf_counter() - t0
 
+    r.SetOption(api.OPT_SORT_MODE, api.SORT_LSD if args.sort_mode == "lsd" else api.SORT_BINNED)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
 
     def frame():
@@ -270,13 +280,23 @@ def run_ours(args, rank, local_rank, world):
 
     n, v, d = int(st.num_gaussians), int(st.num_visible), int(st.num_instances)
     tiles = int(st.tiles_x * st.tiles_y)
-    ab = algorithmic_bytes(n, v, d, int(st.sh_mode), int(st.sort_passes), tiles, WIDTH * HEIGHT, w["fp16"])
+    binned = int(st.sort_mode) == api.SORT_BINNED
+    ab = algorithmic_bytes(n, v, d, int(st.sh_mode), int(st.sort_passes), tiles, WIDTH * HEIGHT, w["fp16"], binned)
     peak, peak_src = measured_peak_gbs()
-    stage = {"project": stages[0], "sort_histogram": stages[1], "sort_passes_total": stages[2], "tile_ranges": stages[3],
-             "composite": stages[4], "frame": stages[7]}
-    pass_ms = stages[2] / max(int(st.sort_passes), 1)
-    cand = {"composite": (stages[4], ab["composite"], stages[4]), "sort_onesweep": (stages[2], ab["sort_pass"], pass_ms),
-            "project": (stages[0], ab["project"], stages[0])}
+    # cand: kernel -> (time it takes in a step, algorithmic bytes per launch, average launch duration)
+    if binned:
+        stage = {"project": stages[0], "bin_scatter": stages[1], "segment_sort": stages[2], "composite": stages[4], "frame": stages[7]}
+        cand = {"composite": (stages[4], ab["composite"], stages[4]), "project": (stages[0], ab["project"], stages[0]),
+                "segment_sort": (stages[2], ab["segment_sort"], stages[2]), "bin_scatter": (stages[1], ab["bin_scatter"], stages[1])}
+        stage_gbs = {k: (ab[k] / (stage[k] * 1e-3) / 1e9 if stage[k] > 0 else None) for k in ("project", "bin_scatter", "segment_sort", "composite")}
+    else:
+        stage = {"project": stages[0], "sort_histogram": stages[1], "sort_passes_total": stages[2], "tile_ranges": stages[3],
+                 "composite": stages[4], "frame": stages[7]}
+        pass_ms = stages[2] / max(int(st.sort_passes), 1)
+        cand = {"composite": (stages[4], ab["composite"], stages[4]), "sort_onesweep": (stages[2], ab["sort_pass"], pass_ms),
+                "project": (stages[0], ab["project"], stages[0])}
+        stage_gbs = {k: (ab[k] / (stage[k] * 1e-3) / 1e9 if stage[k] > 0 else None) for k in ("project", "sort_histogram", "tile_ranges", "composite")}
+        stage_gbs["sort_pass"] = ab["sort_pass"] / (pass_ms * 1e-3) / 1e9 if pass_ms > 0 else None
     dom = max(cand, key=lambda k: cand[k][0])
     dom_total, dom_bytes, dom_launch_ms = cand[dom]
     achieved = dom_bytes / (dom_launch_ms * 1e-3) / 1e9 if dom_launch_ms > 0 else 0.0
@@ -296,7 +316,7 @@ def run_ours(args, rank, local_rank, world):
         "config": {"workload": f"{args.workload}: {w['cfg']} of BASELINE.json -- {n} synthetic gaussians (seed {w['seed']}), SH degree {w['deg']}, "
                                f"{WIDTH}x{HEIGHT}, {'fp16' if w['fp16'] else 'fp32'} framebuffer, one view per GPU",
                    "l2": "flushed between timed frames (256 MiB memset, untimed); e2e loop: per-frame working set > L2",
-                   "tile": 16, "early_out_T": 1e-4, "sort_bits": int(st.sort_bits), "sort_passes": int(st.sort_passes),
+                   "tile": 16, "early_out_T": 1e-4, "sort": "binned: MSD by tile id + per-tile smem sort" if binned else "lsd: device-wide onesweep", "sort_bits": int(st.sort_bits), "sort_passes": int(st.sort_passes),
                    "visible": v, "tile_instances": d, "parallelism": f"views x{world}"},
         "frames_per_s": args.steps * world / secs,
         "sort_gkeys_per_s": (d / ((stages[1] + stages[2]) * 1e-3) / 1e9) if (stages[1] + stages[2]) > 0 else None,
@@ -310,10 +330,9 @@ def run_ours(args, rank, local_rank, world):
                      "frame": {"algorithmic_bytes": ab["frame"], "achieved": ab["frame"] / (stages[7] * 1e-3) / 1e9 if stages[7] > 0 else None,
                                "frac": ab["frame"] / (stages[7] * 1e-3) / 1e9 / peak if stages[7] > 0 else None}},
         "stage_ms": {k: float(x) for k, x in stage.items()},
-        "stage_gbs": {k: (ab[k] / (stage[k] * 1e-3) / 1e9 if stage[k] > 0 else None) for k in ("project", "sort_histogram", "tile_ranges", "composite")},
+        "stage_gbs": stage_gbs,
         "wall_s_timed_loop": wall, "load_s": load_s, "broadcast_ms": broadcast_ms,
     }
-    out["stage_gbs"]["sort_pass"] = ab["sort_pass"] / (pass_ms * 1e-3) / 1e9 if pass_ms > 0 else None
     if world == 1 and not args.no_cpu_baseline:
         out["cpu_baseline"] = cpu_baseline(args.workload, steps=2, warmup=1)
     return out
@@ -376,11 +395,12 @@ def run_reference(args, rank, world):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="1m_deg0", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--sort-mode", default="lsd", choices=["binned", "lsd"])
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))

@@ -118,8 +118,10 @@ typedef struct spl_stats {
     uint32_t tiles_x, tiles_y, tile_size;
     uint32_t sort_passes, sort_bits;
     uint32_t sh_mode;          /* 0 = DC only, 1 = degree 1 (base layout), 3 = degree 3 (FULL_SH) */
+    uint32_t sort_mode;        /* SPL_SORT_* the last Sort used */
     uint32_t kernel_launches;  /* kernels launched by the last Sort+Render */
-    float stage_ms[8];         /* when profiling is on: project, histogram, sort, ranges, composite, 0,0, total */
+    float stage_ms[8];         /* profiling on: [0] project [1] LSD: histogram | binned: scan+scatter [2] LSD: scatter passes |
+                                  binned: segment sort [3] LSD: tile ranges [4] composite [7] whole frame */
 } spl_stats;
 SPL_API int spl_renderer_stats(spl_renderer*, spl_stats* out); /* synchronizes the stream */
 SPL_API int spl_renderer_reserve(spl_renderer*, uint64_t instance_capacity);
@@ -127,7 +129,12 @@ SPL_API int spl_renderer_reserve(spl_renderer*, uint64_t instance_capacity);
 enum {
     SPL_OPT_EARLY_OUT_T = 0,  /* stop a pixel when its transmittance drops below this (default 1e-4; 0 = exact) */
     SPL_OPT_PROFILE = 1,      /* 1: bracket stages with CUDA events (stage_ms) */
-    SPL_OPT_INSTANCES_PER_GAUSSIAN = 2 /* initial capacity factor, before init (default 16) */
+    SPL_OPT_INSTANCES_PER_GAUSSIAN = 2, /* initial capacity factor, before init (default 16) */
+    SPL_OPT_SORT_MODE = 3     /* SPL_SORT_LSD (default) or SPL_SORT_BINNED; both give bit-identical tile lists */
+};
+enum {
+    SPL_SORT_BINNED = 0, /* MSD: counting sort on the tile id, then per-tile shared-memory sort of (depthKey, id) */
+    SPL_SORT_LSD = 1     /* device-wide onesweep LSD radix sort of the packed (tile << 32 | depthKey) u64 keys */
 };
 SPL_API int spl_renderer_set_option(spl_renderer*, int option, double value);
 

@@ -15,6 +15,9 @@ FB_FP16 = 1
 OPT_EARLY_OUT_T = 0
 OPT_PROFILE = 1
 OPT_INSTANCES_PER_GAUSSIAN = 2
+OPT_SORT_MODE = 3
+SORT_BINNED = 0
+SORT_LSD = 1
 
 TAP_RECORDS = 0
 TAP_KEYS = 1
@@ -40,7 +43,7 @@ class Stats(C.Structure):
         ("num_gaussians", C.c_uint64), ("num_visible", C.c_uint64), ("num_instances", C.c_uint64),
         ("instance_capacity", C.c_uint64), ("overflow", C.c_uint32),
         ("tiles_x", C.c_uint32), ("tiles_y", C.c_uint32), ("tile_size", C.c_uint32),
-        ("sort_passes", C.c_uint32), ("sort_bits", C.c_uint32), ("sh_mode", C.c_uint32),
+        ("sort_passes", C.c_uint32), ("sort_bits", C.c_uint32), ("sh_mode", C.c_uint32), ("sort_mode", C.c_uint32),
         ("kernel_launches", C.c_uint32), ("stage_ms", C.c_float * 8),
     ]
 

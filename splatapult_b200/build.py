@@ -31,6 +31,7 @@ CU_SOURCES = {
     "pack.cu": [],
     "project.cu": ["-fmad=false"],
     "radix_sort.cu": [],
+    "binsort.cu": [],
     "composite.cu": [],
     "renderer.cu": [],
     "capi.cu": [],

@@ -27,6 +27,11 @@ constexpr uint32_t kFlagMask = 3u << 30;
 constexpr uint32_t kValueMask = ~kFlagMask;
 constexpr uint64_t kMaxInstances = (1ull << 30) - 1;
 
+// per-tile segment sort (binsort.cu): segments up to kSegSortSmallCap are sorted by a 256-thread CTA in 2 x 16 KiB
+// of static shared memory, up to kSegSortLargeCap by a 1024-thread CTA in 2 x 96 KiB, longer ones through global memory
+constexpr int kSegSortSmallCap = 2048;
+constexpr int kSegSortLargeCap = 12288;
+
 // ---------------------------------------------------------------------------------------------------
 // per-frame constants (host computes them exactly like the reference's CPU side does:
 // view = inverse(cameraMat), mvp = projMat * view   src/splatrenderer.cpp:161,175,327-328)
@@ -77,7 +82,8 @@ struct FrameCounters
     unsigned int overflow;
     unsigned int projectTicket;         // dynamic block ids of the projection kernel
     unsigned int sortTickets[kMaxSortPasses];
-    unsigned int pad[2];
+    unsigned int largeTiles;            // tiles whose segment exceeds kSegSortSmallCap (binned sort)
+    unsigned int pad[1];
 };
 
 // ---------------------------------------------------------------------------------------------------

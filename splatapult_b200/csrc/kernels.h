@@ -20,6 +20,18 @@ uint32_t project_num_blocks(uint32_t n);
 cudaError_t launch_project(const PackedCloud& cloud, const FrameConstants& fc, ProjRecord* rec, unsigned long long* keys, uint32_t* vals,
                            FrameCounters* ctr, unsigned long long* scanState, uint32_t capacity, cudaStream_t stream);
 
+cudaError_t launch_project_bin(const PackedCloud& cloud, const FrameConstants& fc, ProjRecord* rec, uint4* side, uint32_t* tileCount,
+                               FrameCounters* ctr, cudaStream_t stream);
+cudaError_t launch_bin_instances(const uint4* side, uint32_t n, int tilesX, uint32_t* tileCursor, unsigned long long* pairs, uint32_t capacity,
+                                 cudaStream_t stream);
+
+// ---- binsort.cu : MSD-by-tile frame sort (tile scan + per-segment shared-memory sort)
+cudaError_t launch_tile_scan(const uint32_t* tileCount, uint32_t numTiles, uint2* ranges, uint32_t* tileCursor, uint32_t* largeList,
+                             FrameCounters* ctr, uint32_t capacity, cudaStream_t stream);
+// scratch: a second array of the same size, used only by segments too long for shared memory
+cudaError_t launch_segment_sort(unsigned long long* pairs, unsigned long long* scratch, const uint2* ranges, uint32_t numTiles,
+                                const uint32_t* largeList, const FrameCounters* ctr, int numSMs, cudaStream_t stream);
+
 // ---- radix_sort.cu : device-wide LSD radix sort of (u64 key, u32 value) pairs, 8-bit digits, onesweep style
 struct SortWorkspace
 {
@@ -44,7 +56,9 @@ cudaError_t launch_sort_passes(unsigned long long* keysA, uint32_t* valsA, unsig
 // ---- composite.cu
 cudaError_t launch_tile_ranges(const unsigned long long* sortedKeys, const uint32_t* nDevice, uint64_t capacity, uint2* ranges,
                                uint32_t numTiles, int numSMs, cudaStream_t stream);
-cudaError_t launch_composite(const uint2* ranges, const uint32_t* sortedVals, const ProjRecord* rec, void* framebuffer, int fbFormat,
+// ids: gaussian id of list entry k is ids[k * idStrideWords] (1: u32 payload array of the LSD sort, 2: low word of the
+// binned sort's u64 (depthKey << 32 | id) pairs)
+cudaError_t launch_composite(const uint2* ranges, const uint32_t* ids, int idStrideWords, const ProjRecord* rec, void* framebuffer, int fbFormat,
                              int width, int height, int tilesX, int tilesY, float earlyOutT, cudaStream_t stream);
 
 }  // namespace splat

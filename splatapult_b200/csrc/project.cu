@@ -124,24 +124,21 @@ __device__ __forceinline__ void radiance(const PackedCloud& cloud, uint32_t i, f
     }
 }
 
-template <int SH_MODE>
-__global__ void __launch_bounds__(kProjThreads)
-k_project(const PackedCloud cloud, const __grid_constant__ FrameConstants fc, ProjRecord* __restrict__ rec,
-          unsigned long long* __restrict__ keys, uint32_t* __restrict__ vals, FrameCounters* __restrict__ ctr,
-          unsigned long long* __restrict__ scanState, uint32_t capacity)
+// K1 + K5 + K6 for gaussian i: writes its projected record, returns its pre-sort key and tile rectangle
+struct Projected
 {
-    __shared__ uint32_t sBlockId;
-    __shared__ uint32_t sWarpTotal[kProjThreads / 32];
-    __shared__ unsigned long long sBlockBase;
+    uint32_t count;   // tiles touched (0: culled, or too faint to reach the 1/256 threshold anywhere)
+    uint32_t x0, y0;  // first tile column / row
+    uint32_t w, h;    // rectangle size in tiles
+    uint32_t refKey;  // 0xFFFFFFFF - uint(depth/far * 2^32)
+    bool visible;
+};
 
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (tid == 0) sBlockId = atomicAdd(&ctr->projectTicket, 1u);  // dynamic id: predecessors are resident or done
-    __syncthreads();
-    const uint32_t vbid = sBlockId;
-    const uint32_t i = vbid * kProjThreads + tid;
-    const bool inRange = i < cloud.n;
-
-    uint32_t count = 0, rect = 0, refKey = 0;
+template <int SH_MODE>
+__device__ __forceinline__ Projected project_gaussian(const PackedCloud& cloud, const FrameConstants& fc, ProjRecord* __restrict__ rec, uint32_t i,
+                                                      bool inRange)
+{
+    uint32_t count = 0, rx0 = 0, ry0 = 0, rw = 0, rh = 0, refKey = 0;
     bool visible = false;
 
     if (inRange)
@@ -237,13 +234,38 @@ k_project(const PackedCloud cloud, const __grid_constant__ FrameConstants fc, Pr
                         const uint32_t ty0 = (uint32_t)fy0 >> kTileShift, ty1 = (uint32_t)fy1 >> kTileShift;
                         const uint32_t w = tx1 - tx0 + 1, h = ty1 - ty0 + 1;
                         count = w * h;
-                        rect = tx0 | (ty0 << 10) | ((w - 1) << 20);
+                        rx0 = tx0; ry0 = ty0; rw = w; rh = h;
                     }
                 }
             }
         }
         reinterpret_cast<float4*>(rec + i)[2] = q2;  // {b, alpha, key, visible}: always written
     }
+
+    Projected out;
+    out.count = count; out.x0 = rx0; out.y0 = ry0; out.w = rw; out.h = rh; out.refKey = refKey; out.visible = visible;
+    return out;
+}
+
+template <int SH_MODE>
+__global__ void __launch_bounds__(kProjThreads)
+k_project(const PackedCloud cloud, const __grid_constant__ FrameConstants fc, ProjRecord* __restrict__ rec,
+          unsigned long long* __restrict__ keys, uint32_t* __restrict__ vals, FrameCounters* __restrict__ ctr,
+          unsigned long long* __restrict__ scanState, uint32_t capacity)
+{
+    __shared__ uint32_t sBlockId;
+    __shared__ uint32_t sWarpTotal[kProjThreads / 32];
+    __shared__ unsigned long long sBlockBase;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) sBlockId = atomicAdd(&ctr->projectTicket, 1u);  // dynamic id: predecessors are resident or done
+    __syncthreads();
+    const uint32_t vbid = sBlockId;
+    const uint32_t i = vbid * kProjThreads + tid;
+    const Projected pg = project_gaussian<SH_MODE>(cloud, fc, rec, i, i < cloud.n);
+    const uint32_t count = pg.count, refKey = pg.refKey;
+    const uint32_t rect = pg.x0 | (pg.y0 << 10) | ((pg.w ? pg.w - 1 : 0) << 20);
+    const bool visible = pg.visible;
 
     // ---- block-wide exclusive scan of the tile counts
     uint32_t incl = count;
@@ -351,6 +373,133 @@ k_project(const PackedCloud cloud, const __grid_constant__ FrameConstants fc, Pr
             vals[oOff + k] = oId;
         }
     }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// binned (MSD-by-tile) variant: same projection, but instead of emitting keys it leaves a 16-byte side record
+// {x0|y0<<16, w|h<<16, depthKey, count} per gaussian and counts the instances of every tile with one RED per
+// instance; key slots are handed out later, per tile (binsort.cu).
+// ---------------------------------------------------------------------------------------------------
+template <int SH_MODE>
+__global__ void __launch_bounds__(kProjThreads)
+k_project_bin(const PackedCloud cloud, const __grid_constant__ FrameConstants fc, ProjRecord* __restrict__ rec, uint4* __restrict__ side,
+              uint32_t* __restrict__ tileCount, FrameCounters* __restrict__ ctr)
+{
+    const int lane = threadIdx.x & 31;
+    const uint32_t i = blockIdx.x * kProjThreads + threadIdx.x;
+    const bool inRange = i < cloud.n;
+    const Projected pg = project_gaussian<SH_MODE>(cloud, fc, rec, i, inRange);
+    if (inRange) side[i] = make_uint4(pg.x0 | (pg.y0 << 16), pg.w | (pg.h << 16), pg.refKey, pg.count);
+
+    const uint32_t nVisibleWarp = __popc(__ballot_sync(0xffffffffu, pg.visible));
+    uint32_t incl = pg.count;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1)
+    {
+        const uint32_t v = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += v;
+    }
+    const uint32_t wex = incl - pg.count;
+    const uint32_t T = __shfl_sync(0xffffffffu, incl, 31);
+    if (lane == 0)
+    {
+        if (nVisibleWarp) atomicAdd(&ctr->visible, nVisibleWarp);
+        if (T) atomicAdd(&ctr->totalInstances, (unsigned long long)T);
+    }
+    const uint32_t rectXY = pg.x0 | (pg.y0 << 16);
+    const uint32_t tilesX = (uint32_t)fc.tilesX;
+    for (uint32_t j0 = 0; j0 < T; j0 += 32)
+    {
+        const uint32_t j = j0 + lane;
+        int owner = 0;
+#pragma unroll
+        for (int s = 16; s; s >>= 1)
+        {
+            const int cand = owner + s;
+            const uint32_t v = __shfl_sync(0xffffffffu, wex, cand);
+            if (v <= j) owner = cand;
+        }
+        const uint32_t oBase = __shfl_sync(0xffffffffu, wex, owner);
+        const uint32_t oXY = __shfl_sync(0xffffffffu, rectXY, owner);
+        const uint32_t oW = __shfl_sync(0xffffffffu, pg.w, owner);
+        if (j < T)
+        {
+            const uint32_t k = j - oBase;
+            const uint32_t row = k / oW, col = k - row * oW;
+            const uint32_t tile = ((oXY >> 16) + row) * tilesX + ((oXY & 0xffffu) + col);
+            atomicAdd(tileCount + tile, 1u);  // result unused: compiles to RED
+        }
+    }
+}
+
+// scatter: every instance takes the next free slot of its tile's segment (order inside a segment is arbitrary
+// here; the per-tile sort orders by (depthKey, id), which is total, so the final lists are deterministic)
+__global__ void __launch_bounds__(kProjThreads)
+k_bin_instances(const uint4* __restrict__ side, uint32_t n, int tilesX, uint32_t* __restrict__ tileCursor, unsigned long long* __restrict__ pairs,
+                uint32_t capacity)
+{
+    const int lane = threadIdx.x & 31;
+    const uint32_t i = blockIdx.x * kProjThreads + threadIdx.x;
+    uint4 sd = make_uint4(0, 0, 0, 0);
+    if (i < n) sd = __ldg(side + i);
+    const uint32_t count = sd.w;
+    uint32_t incl = count;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1)
+    {
+        const uint32_t v = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += v;
+    }
+    const uint32_t wex = incl - count;
+    const uint32_t T = __shfl_sync(0xffffffffu, incl, 31);
+    for (uint32_t j0 = 0; j0 < T; j0 += 32)
+    {
+        const uint32_t j = j0 + lane;
+        int owner = 0;
+#pragma unroll
+        for (int s = 16; s; s >>= 1)
+        {
+            const int cand = owner + s;
+            const uint32_t v = __shfl_sync(0xffffffffu, wex, cand);
+            if (v <= j) owner = cand;
+        }
+        const uint32_t oBase = __shfl_sync(0xffffffffu, wex, owner);
+        const uint32_t oXY = __shfl_sync(0xffffffffu, sd.x, owner);
+        const uint32_t oW = __shfl_sync(0xffffffffu, sd.y, owner) & 0xffffu;
+        const uint32_t oKey = __shfl_sync(0xffffffffu, sd.z, owner);
+        const uint32_t oId = __shfl_sync(0xffffffffu, i, owner);
+        if (j < T)
+        {
+            const uint32_t k = j - oBase;
+            const uint32_t row = k / oW, col = k - row * oW;
+            const uint32_t tile = ((oXY >> 16) + row) * (uint32_t)tilesX + ((oXY & 0xffffu) + col);
+            const uint32_t slot = atomicAdd(tileCursor + tile, 1u);
+            if (slot < capacity) pairs[slot] = ((unsigned long long)oKey << 32) | oId;
+        }
+    }
+}
+
+cudaError_t launch_project_bin(const PackedCloud& cloud, const FrameConstants& fc, ProjRecord* rec, uint4* side, uint32_t* tileCount,
+                               FrameCounters* ctr, cudaStream_t stream)
+{
+    const uint32_t blocks = project_num_blocks(cloud.n);
+    if (blocks == 0) return cudaSuccess;
+    switch (cloud.shMode)
+    {
+    case 0: k_project_bin<0><<<blocks, kProjThreads, 0, stream>>>(cloud, fc, rec, side, tileCount, ctr); break;
+    case 1: k_project_bin<1><<<blocks, kProjThreads, 0, stream>>>(cloud, fc, rec, side, tileCount, ctr); break;
+    default: k_project_bin<3><<<blocks, kProjThreads, 0, stream>>>(cloud, fc, rec, side, tileCount, ctr); break;
+    }
+    return cudaGetLastError();
+}
+
+cudaError_t launch_bin_instances(const uint4* side, uint32_t n, int tilesX, uint32_t* tileCursor, unsigned long long* pairs, uint32_t capacity,
+                                 cudaStream_t stream)
+{
+    const uint32_t blocks = project_num_blocks(n);
+    if (blocks == 0) return cudaSuccess;
+    k_bin_instances<<<blocks, kProjThreads, 0, stream>>>(side, n, tilesX, tileCursor, pairs, capacity);
+    return cudaGetLastError();
 }
 
 cudaError_t launch_project(const PackedCloud& cloud, const FrameConstants& fc, ProjRecord* rec, unsigned long long* keys, uint32_t* vals,

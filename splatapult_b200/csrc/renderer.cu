@@ -12,6 +12,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <vector>
 
 #include "kernels.h"
 #include "splat_b200.h"
@@ -37,6 +38,7 @@ struct RendererImpl
     double earlyOutT = 1e-4;
     bool profile = false;
     double instancesPerGaussian = 16.0;
+    int sortMode = SPL_SORT_LSD;
 
     // cloud
     bool initialized = false;
@@ -57,6 +59,8 @@ struct RendererImpl
     unsigned long long* dScan = nullptr;
     uint32_t* dStatus = nullptr;
     uint2* dRanges = nullptr;
+    uint32_t* dTileCtl = nullptr;  // tileCount | tileCursor | largeList, rangesTiles words each
+    uint4* dSide = nullptr;        // per-gaussian {rect, depthKey, count} of the binned sort
     uint32_t rangesTiles = 0;
     void* dFb = nullptr;
     size_t fbBytes = 0;
@@ -67,6 +71,7 @@ struct RendererImpl
     FrameConstants fc{};
     float lastArgs[16 + 16 + 4 + 2] = {};
     int sortPasses = 0, sortBits = 0;
+    int frameSortMode = SPL_SORT_LSD;  // sort path the last Sort() used
     uint32_t launches = 0;
     cudaEvent_t ev[7] = {};
     bool evCreated = false;
@@ -100,8 +105,8 @@ struct RendererImpl
         cudaSetDevice(device);
         if (stream) cudaStreamSynchronize(stream);
         freeFrameBuffers();
-        cudaFree(dPlanes); cudaFree(dRec); cudaFree(dControl); cudaFree(dRanges); cudaFree(dFb);
-        dPlanes = nullptr; dRec = nullptr; dControl = nullptr; dRanges = nullptr; dFb = nullptr;
+        cudaFree(dPlanes); cudaFree(dRec); cudaFree(dControl); cudaFree(dRanges); cudaFree(dFb); cudaFree(dTileCtl); cudaFree(dSide);
+        dPlanes = nullptr; dRec = nullptr; dControl = nullptr; dRanges = nullptr; dFb = nullptr; dTileCtl = nullptr; dSide = nullptr;
         if (evCreated)
             for (auto& e : ev) cudaEventDestroy(e);
         evCreated = false;
@@ -157,8 +162,8 @@ struct RendererImpl
 
         // drop any previous cloud
         CU_TRY(cudaStreamSynchronize(stream));
-        cudaFree(dPlanes); cudaFree(dRec); cudaFree(dControl);
-        dPlanes = nullptr; dRec = nullptr; dControl = nullptr;
+        cudaFree(dPlanes); cudaFree(dRec); cudaFree(dControl); cudaFree(dSide);
+        dPlanes = nullptr; dRec = nullptr; dControl = nullptr; dSide = nullptr;
 
         n = (uint32_t)count;
         srgb = srgbIn;
@@ -178,6 +183,7 @@ struct RendererImpl
         CU_TRY(pack_cloud(dAos, n, (uint32_t)stride, shMode, dPlanes, &cloud, stream));
         CU_TRY(cudaMalloc(&dRec, std::max<size_t>(n, 1) * sizeof(ProjRecord)));
         CU_TRY(cudaMemsetAsync(dRec, 0, std::max<size_t>(n, 1) * sizeof(ProjRecord), stream));
+        CU_TRY(cudaMalloc(&dSide, std::max<size_t>(n, 1) * sizeof(uint4)));
         if (int rc = reserve((uint64_t)std::ceil(std::max(1.0, instancesPerGaussian) * std::max<uint32_t>(n, 1)))) return rc;
         CU_TRY(cudaStreamSynchronize(stream));
         initialized = true;
@@ -233,8 +239,11 @@ struct RendererImpl
         {
             CU_TRY(cudaStreamSynchronize(stream));
             cudaFree(dRanges);
+            cudaFree(dTileCtl);
             dRanges = nullptr;
+            dTileCtl = nullptr;
             CU_TRY(cudaMalloc(&dRanges, (size_t)numTiles * sizeof(uint2)));
+            CU_TRY(cudaMalloc(&dTileCtl, (size_t)numTiles * 3 * sizeof(uint32_t)));
             rangesTiles = numTiles;
         }
         int tileBits = 0;
@@ -248,22 +257,42 @@ struct RendererImpl
             evCreated = true;
         }
         launches = 0;
-        int sortLaunches = 0;
+        frameSortMode = sortMode;
         if (profile) CU_TRY(cudaEventRecord(ev[0], stream));
         CU_TRY(cudaMemsetAsync(dControl, 0, controlBytes, stream));
-        CU_TRY(launch_project(cloud, fc, dRec, dKeysA, dValsA, dCtr, dScan, (uint32_t)capacity, stream));
-        launches += n ? 1 : 0;
-        if (profile) CU_TRY(cudaEventRecord(ev[1], stream));
-        SortWorkspace ws{dHist, dStatus, dCtr->sortTickets, capacity};
-        CU_TRY(launch_sort_histogram(dKeysA, &dCtr->usedInstances, capacity, 0, sortBits, ws, numSMs, stream));
-        if (profile) CU_TRY(cudaEventRecord(ev[6], stream));
-        CU_TRY(launch_sort_passes(dKeysA, dValsA, dKeysB, dValsB, &dCtr->usedInstances, capacity, 0, sortBits, ws, numSMs, stream));
-        sortLaunches = 1 + sortPasses;
-        launches += sortLaunches;
-        if (profile) CU_TRY(cudaEventRecord(ev[2], stream));
-        CU_TRY(launch_tile_ranges(sortedKeys(), &dCtr->usedInstances, capacity, dRanges, numTiles, numSMs, stream));
-        launches += 1;
-        if (profile) CU_TRY(cudaEventRecord(ev[3], stream));
+        if (frameSortMode == SPL_SORT_BINNED)
+        {
+            // MSD by tile: count -> scan (= tile ranges) -> scatter into segments -> per-segment shared-memory sort
+            uint32_t* tileCount = dTileCtl;
+            uint32_t* tileCursor = dTileCtl + rangesTiles;
+            uint32_t* largeList = dTileCtl + 2 * (size_t)rangesTiles;
+            CU_TRY(cudaMemsetAsync(tileCount, 0, (size_t)numTiles * sizeof(uint32_t), stream));
+            CU_TRY(launch_project_bin(cloud, fc, dRec, dSide, tileCount, dCtr, stream));
+            if (profile) CU_TRY(cudaEventRecord(ev[1], stream));
+            CU_TRY(launch_tile_scan(tileCount, numTiles, dRanges, tileCursor, largeList, dCtr, (uint32_t)capacity, stream));
+            CU_TRY(launch_bin_instances(dSide, n, tilesX, tileCursor, dKeysA, (uint32_t)capacity, stream));
+            if (profile) CU_TRY(cudaEventRecord(ev[6], stream));
+            CU_TRY(launch_segment_sort(dKeysA, dKeysB, dRanges, numTiles, largeList, dCtr, numSMs, stream));
+            if (profile) CU_TRY(cudaEventRecord(ev[2], stream));
+            if (profile) CU_TRY(cudaEventRecord(ev[3], stream));
+            launches += (n ? 2 : 0) + 3;
+        }
+        else
+        {
+            // LSD: device-wide onesweep radix sort of the packed u64 keys, then boundary detection
+            CU_TRY(launch_project(cloud, fc, dRec, dKeysA, dValsA, dCtr, dScan, (uint32_t)capacity, stream));
+            launches += n ? 1 : 0;
+            if (profile) CU_TRY(cudaEventRecord(ev[1], stream));
+            SortWorkspace ws{dHist, dStatus, dCtr->sortTickets, capacity};
+            CU_TRY(launch_sort_histogram(dKeysA, &dCtr->usedInstances, capacity, 0, sortBits, ws, numSMs, stream));
+            if (profile) CU_TRY(cudaEventRecord(ev[6], stream));
+            CU_TRY(launch_sort_passes(dKeysA, dValsA, dKeysB, dValsB, &dCtr->usedInstances, capacity, 0, sortBits, ws, numSMs, stream));
+            launches += 1 + sortPasses;
+            if (profile) CU_TRY(cudaEventRecord(ev[2], stream));
+            CU_TRY(launch_tile_ranges(sortedKeys(), &dCtr->usedInstances, capacity, dRanges, numTiles, numSMs, stream));
+            launches += 1;
+            if (profile) CU_TRY(cudaEventRecord(ev[3], stream));
+        }
         haveSort = true;
         return ok();
     }
@@ -291,7 +320,8 @@ struct RendererImpl
         }
         fbW = fc.width; fbH = fc.height;
         if (profile) CU_TRY(cudaEventRecord(ev[4], stream));
-        CU_TRY(launch_composite(dRanges, sortedVals(), dRec, dFb, fbFormat, fc.width, fc.height, fc.tilesX, fc.tilesY, (float)earlyOutT, stream));
+        const bool binned = frameSortMode == SPL_SORT_BINNED;
+        CU_TRY(launch_composite(dRanges, binned ? reinterpret_cast<const uint32_t*>(dKeysA) : sortedVals(), binned ? 2 : 1, dRec, dFb, fbFormat, fc.width, fc.height, fc.tilesX, fc.tilesY, (float)earlyOutT, stream));
         launches += 1;
         if (profile) CU_TRY(cudaEventRecord(ev[5], stream));
         haveRender = true;
@@ -344,7 +374,8 @@ struct RendererImpl
         out->instance_capacity = capacity;
         out->overflow = c.overflow;
         out->tiles_x = fc.tilesX; out->tiles_y = fc.tilesY; out->tile_size = kTileSize;
-        out->sort_passes = sortPasses; out->sort_bits = sortBits;
+        out->sort_passes = frameSortMode == SPL_SORT_BINNED ? 1 : sortPasses; out->sort_bits = sortBits;
+        out->sort_mode = frameSortMode;
         out->sh_mode = cloud.shMode;
         out->kernel_launches = launches;
         if (profile && evCreated && haveSort)
@@ -372,6 +403,24 @@ struct RendererImpl
         if (int rc = readCounters(&c)) return rc;
         const void* src = nullptr;
         size_t have = 0;
+        if (frameSortMode == SPL_SORT_BINNED && (what == SPL_TAP_KEYS || what == SPL_TAP_VALS))
+        {
+            // binned sort keeps (depthKey << 32 | id) per tile segment: rebuild the LSD view (tile << 32 | depthKey), id
+            const size_t d = c.usedInstances, tiles = (size_t)fc.tilesX * fc.tilesY;
+            if (bytes < d * (what == SPL_TAP_KEYS ? 8 : 4)) return fail(SPL_ERR_ARG, "tap buffer too small");
+            std::vector<unsigned long long> pairs(d);
+            std::vector<uint2> rg(tiles);
+            if (d) CU_TRY(cudaMemcpyAsync(pairs.data(), dKeysA, d * 8, cudaMemcpyDeviceToHost, stream));
+            CU_TRY(cudaMemcpyAsync(rg.data(), dRanges, tiles * sizeof(uint2), cudaMemcpyDeviceToHost, stream));
+            CU_TRY(cudaStreamSynchronize(stream));
+            for (size_t t = 0; t < tiles; t++)
+                for (uint32_t k = rg[t].x; k < rg[t].y; k++)
+                {
+                    if (what == SPL_TAP_KEYS) static_cast<unsigned long long*>(host)[k] = ((unsigned long long)t << 32) | (pairs[k] >> 32);
+                    else static_cast<uint32_t*>(host)[k] = (uint32_t)pairs[k];
+                }
+            return ok();
+        }
         switch (what)
         {
         case SPL_TAP_RECORDS: src = dRec; have = (size_t)n * sizeof(ProjRecord); break;
@@ -477,6 +526,11 @@ bool SplatRenderer::SetOption(int option, double value)
     case SPL_OPT_EARLY_OUT_T: impl->earlyOutT = value; break;
     case SPL_OPT_PROFILE: impl->profile = value != 0.0; break;
     case SPL_OPT_INSTANCES_PER_GAUSSIAN: impl->instancesPerGaussian = value; break;
+    case SPL_OPT_SORT_MODE:
+        if (value != SPL_SORT_BINNED && value != SPL_SORT_LSD) { status = SPL_ERR_ARG; error = "unknown sort mode"; return false; }
+        impl->sortMode = (int)value;
+        impl->haveSort = false;
+        break;
     default: status = SPL_ERR_ARG; error = "unknown option"; return false;
     }
     status = 0;

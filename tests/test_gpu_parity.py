@@ -19,10 +19,27 @@ pytestmark = pytest.mark.gpu
 NF = [scenes.Z_NEAR, scenes.Z_FAR]
 
 
+SORT_MODE = api.SORT_BINNED
+
+
+@pytest.fixture(params=[api.SORT_BINNED, api.SORT_LSD], ids=["binned", "lsd"], autouse=True)
+def sort_mode(request):
+    """every test runs on both frame-sort paths: MSD-by-tile (default) and the device-wide LSD onesweep"""
+    global SORT_MODE
+    SORT_MODE = request.param
+    return request.param
+
+
+def _new(splat, **kw):
+    r = splat.SplatRenderer(**kw)
+    r.SetOption(api.OPT_SORT_MODE, SORT_MODE)
+    return r
+
+
 def _renderer(splat, aos, full, fb_format=0, early_out=None):
     gc = splat.GaussianCloud()
     gc.SetRawData(aos, full)
-    r = splat.SplatRenderer(fb_format=fb_format)
+    r = _new(splat, fb_format=fb_format)
     assert r.Init(gc, False, False), getattr(r, "last_error", "")
     if early_out is not None:
         r.SetOption(api.OPT_EARLY_OUT_T, early_out)
@@ -103,7 +120,7 @@ def test_reference_fixture_config1(splat, oracle, golden_dir):
     g = np.load(os.path.join(golden_dir, "test_ply_640x480.npz"))
     gc = splat.GaussianCloud()
     assert gc.ImportPly(os.path.join(golden_dir, "reference_test.ply"))
-    r = splat.SplatRenderer()
+    r = _new(splat)
     assert r.Init(gc, False, False)
     fb = _frame(r, g["camera"], g["proj"], 640, 480)
     _check_records(r.Tap(api.TAP_RECORDS), g["records"])
@@ -131,7 +148,7 @@ def test_debug_cloud(splat, oracle):
     """InitDebugCloud rendered from translate(0.5, 0.5, 3): stride 244 without full SH."""
     gc = splat.GaussianCloud()
     gc.InitDebugCloud()
-    r = splat.SplatRenderer()
+    r = _new(splat)
     assert r.Init(gc, False, False)
     cam, proj = scenes.translate(0.5, 0.5, 3), scenes.perspective(scenes.FOVY, 640 / 480)
     fb = _frame(r, cam, proj, 640, 480)
@@ -148,7 +165,7 @@ def test_synthetic_scene(splat, oracle, scratch, deg, n, w, h, cam_z):
     scenes.write_synthetic_ply(path, n, deg, seed=101 + deg)
     gc = splat.GaussianCloud()
     assert gc.ImportPly(path)
-    r = splat.SplatRenderer()
+    r = _new(splat)
     assert r.Init(gc, False, False)
     cam, proj = scenes.translate(0, 0, cam_z), scenes.perspective(scenes.FOVY, w / h)
     fb = _frame(r, cam, proj, w, h)
@@ -172,7 +189,7 @@ def test_camera_inside_cloud_culls_and_huge_splats(splat, oracle, scratch):
     path = scenes.write_ply_from_arrays(str(scratch / "inside.ply"), a)
     gc = splat.GaussianCloud()
     assert gc.ImportPly(path)
-    r = splat.SplatRenderer()
+    r = _new(splat)
     assert r.Init(gc, False, False)
     cam = scenes.look_at_camera((0.3, 0.2, 0.1), (1.0, 0.4, -2.0))
     proj = scenes.perspective(scenes.FOVY, 512 / 384)
@@ -191,7 +208,7 @@ def test_capacity_overflow_regrows(splat, oracle, scratch):
     path = scenes.write_ply_from_arrays(str(scratch / "overflow.ply"), a)
     gc = splat.GaussianCloud()
     assert gc.ImportPly(path)
-    r = splat.SplatRenderer()
+    r = _new(splat)
     r.SetOption(api.OPT_INSTANCES_PER_GAUSSIAN, 1.0)
     assert r.Init(gc, False, False)
     cam, proj = scenes.translate(0, 0, 4), scenes.perspective(scenes.FOVY, 640 / 480)
@@ -221,7 +238,7 @@ def test_srgb_mode(splat, oracle, golden_dir):
     g = np.load(os.path.join(golden_dir, "synth_2k_deg3_320x180.npz"))
     gc = splat.GaussianCloud()
     gc.SetRawData(g["aos"], True)
-    r = splat.SplatRenderer()
+    r = _new(splat)
     assert r.Init(gc, True, False)
     fb = _frame(r, g["camera"], g["proj"], 320, 180)
     want, rec, _, _ = oracle.render(g["aos"], True, g["camera"], g["proj"], [0, 0, 320, 180], NF, srgb=True, want_records=True)
@@ -272,7 +289,7 @@ def test_empty_and_all_culled(splat):
 
 def test_error_behaviour(splat, golden_dir):
     g = np.load(os.path.join(golden_dir, "synth_2k_deg3_320x180.npz"))
-    r = splat.SplatRenderer()
+    r = _new(splat)
     with pytest.raises(splat.SplatError):  # Sort before Init
         r.Sort(g["camera"], g["proj"], [0, 0, 320, 180], NF)
     r = _renderer(splat, g["aos"], True)
@@ -285,3 +302,30 @@ def test_error_behaviour(splat, golden_dir):
     gc = splat.GaussianCloud()
     with pytest.raises(splat.SplatError):
         gc.SetRawData(np.zeros((4, 30), np.float32), False)  # stride must be 100 or 244
+
+
+@pytest.mark.parametrize("n,expect_path", [(1500, "small"), (6000, "large-smem"), (40000, "global")])
+def test_dense_tile_segments(splat, oracle, scratch, n, expect_path):
+    """thousands of gaussians inside ONE 16x16 tile: exercises every size class of the per-tile segment sort
+    (<= 2048 and <= 12288 in shared memory, longer through global memory) and deep front-to-back lists."""
+    a = scenes.synthetic_cloud_arrays(n, 0, seed=77, half_extent=0.02)
+    a["log_scale"][:] = np.log(0.004)
+    a["opacity"][:] = -3.0  # alpha ~ 0.047: thousands of layers stay above the transmittance early-out
+    path = scenes.write_ply_from_arrays(str(scratch / f"dense_{n}.ply"), a)
+    gc = splat.GaussianCloud()
+    assert gc.ImportPly(path)
+    r = _new(splat)
+    r.SetOption(api.OPT_INSTANCES_PER_GAUSSIAN, 8.0)
+    assert r.Init(gc, False, False)
+    cam, proj = scenes.translate(0.0, 0.0, 6.0), scenes.perspective(scenes.FOVY, 1.0)
+    fb = _frame(r, cam, proj, 64, 64)
+    aos, full = oracle.import_ply(path, True)
+    want, rec, order, _ = oracle.render(aos, full, cam, proj, [0, 0, 64, 64], NF, want_records=True)
+    _check_records(r.Tap(api.TAP_RECORDS), rec)
+    _check_tile_lists(r, rec, order, 64, 64)
+    ranges = r.Tap(api.TAP_TILE_RANGES)
+    longest = int((ranges[:, 1] - ranges[:, 0]).max())
+    assert {"small": longest <= 2048, "large-smem": 2048 < longest <= 12288, "global": longest > 12288}[expect_path], longest
+    _check_image(fb, want)
+    r.SetOption(api.OPT_EARLY_OUT_T, 0.0)
+    _check_image(_frame(r, cam, proj, 64, 64), want, exact_mode=True)
