@@ -174,26 +174,17 @@ def run_ours(args, rank, local_rank, world):
             raise RuntimeError(r.last_error)
         del gc
     else:
-        meta = [None]
+        from splatapult_b200 import sharding
+
+        host, host_full = None, None
         if rank == 0:
             gc = sp.GaussianCloud(import_full_sh=True, export_full_sh=True)
             if not gc.ImportPly(scene_path(args.workload)):
                 raise RuntimeError(gc.LastError())
-            host = gc.GetRawData()
-            meta = [(gc.GetNumGaussians(), gc.GetStride(), gc.HasFullSH())]
-        dist.broadcast_object_list(meta, src=0)
-        n_gauss, stride, full = meta[0]
-        buf = torch.empty((n_gauss, stride // 4), dtype=torch.float32, device=dev)
-        if rank == 0:
-            buf.copy_(torch.from_numpy(host))
-        torch.cuda.synchronize()
-        dist.barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        dist.broadcast(buf, src=0)  # NCCL over NVLink/NVSwitch, once at start-up
-        e1.record()
-        torch.cuda.synchronize()
-        broadcast_ms = e0.elapsed_time(e1)
+            host, host_full = gc.GetRawData(), gc.HasFullSH()
+        # one ncclBroadcast of the AoS over NVLink/NVSwitch, at start-up only (not in the timed region)
+        buf, full, broadcast_ms = sharding.broadcast_cloud(host, host_full, src=0, device=dev)
+        n_gauss, stride = int(buf.shape[0]), int(buf.shape[1]) * 4
         r.InitFromDevice(buf.data_ptr(), n_gauss, stride, full)
         del buf
     load_s = time.perf_counter() - t0
