@@ -103,10 +103,14 @@ SPL_API int spl_renderer_render(spl_renderer*, const float camera_mat[16], const
 /* the render target of the last Render (device pointer; valid until the next Render / resize / destroy) */
 SPL_API int spl_renderer_framebuffer(spl_renderer*, void** device_ptr, int* width, int* height,
                                      size_t* row_pitch_bytes, int* fb_format);
-/* device->host copy of the target: enqueue on the renderer stream (host should be pinned) ... */
+/* device->host copy of the target: enqueued on the renderer's copy stream after the frame (host should be
+ * pinned); two targets alternate, so the next Sort/Render overlaps the copy ... */
 SPL_API int spl_renderer_read_framebuffer_async(spl_renderer*, void* host, size_t bytes);
 /* ... or copy and wait; re-runs the frame once with a larger capacity if it overflowed */
 SPL_API int spl_renderer_read_framebuffer(spl_renderer*, void* host, size_t bytes);
+/* device-side join: the render stream waits for every framebuffer copy still in flight (no host block) */
+SPL_API int spl_renderer_fence_copies(spl_renderer*);
+/* host waits for the render stream and the copy stream */
 SPL_API int spl_renderer_synchronize(spl_renderer*);
 
 typedef struct spl_stats {
@@ -130,6 +134,7 @@ enum {
     SPL_OPT_EARLY_OUT_T = 0,  /* stop a pixel when its transmittance drops below this (default 1e-4; 0 = exact) */
     SPL_OPT_PROFILE = 1,      /* 1: bracket stages with CUDA events (stage_ms) */
     SPL_OPT_INSTANCES_PER_GAUSSIAN = 2, /* initial capacity factor, before init (default 16) */
+    SPL_OPT_SORT_TILE = 4,    /* keys per onesweep tile: 4096 (default) or 2048 */
     SPL_OPT_SORT_MODE = 3     /* SPL_SORT_LSD (default) or SPL_SORT_BINNED; both give bit-identical tile lists */
 };
 enum {

@@ -42,9 +42,11 @@ public:
 
     // --- explicit replacements for the reference's implicit GL state ---
     bool GetFramebuffer(void** devicePtr, int* width, int* height, size_t* rowPitchBytes, FrameBuffer* format) const;
+    // copies run on an internal copy stream and overlap the next frame (two render targets alternate)
     bool ReadFramebufferAsync(void* host, size_t bytes);
     bool ReadFramebuffer(void* host, size_t bytes);  // waits; transparently re-renders once on capacity overflow
-    bool Synchronize();
+    bool FenceCopies();   // make the render stream wait (device-side) for every copy still in flight
+    bool Synchronize();   // host waits for the render stream and the copy stream
     bool GetStats(spl_stats* out);
     bool Reserve(uint64_t instanceCapacity);
     bool SetOption(int option, double value);

@@ -16,6 +16,7 @@ OPT_EARLY_OUT_T = 0
 OPT_PROFILE = 1
 OPT_INSTANCES_PER_GAUSSIAN = 2
 OPT_SORT_MODE = 3
+OPT_SORT_TILE = 4
 SORT_BINNED = 0
 SORT_LSD = 1
 
@@ -83,6 +84,7 @@ _SIGNATURES = [
                                            C.POINTER(C.c_size_t), C.POINTER(C.c_int)]),
     ("spl_renderer_read_framebuffer_async", C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
     ("spl_renderer_read_framebuffer", C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
+    ("spl_renderer_fence_copies", C.c_int, [C.c_void_p]),
     ("spl_renderer_synchronize", C.c_int, [C.c_void_p]),
     ("spl_renderer_stats", C.c_int, [C.c_void_p, C.POINTER(Stats)]),
     ("spl_renderer_reserve", C.c_int, [C.c_void_p, C.c_uint64]),
@@ -263,6 +265,10 @@ class SplatRenderer:
 
     def ReadFramebufferAsync(self, host_ptr: int, nbytes: int) -> None:
         _check(lib().spl_renderer_read_framebuffer_async(self._h, C.c_void_p(host_ptr), nbytes))
+
+    def FenceCopies(self) -> None:
+        """device-side join: the render stream waits for every framebuffer copy still in flight."""
+        _check(lib().spl_renderer_fence_copies(self._h))
 
     def Synchronize(self) -> None:
         _check(lib().spl_renderer_synchronize(self._h))

@@ -157,6 +157,11 @@ int spl_renderer_read_framebuffer(spl_renderer* h, void* host, size_t bytes)
     if (!h || !host) return set_error(SPL_ERR_ARG, "null argument");
     return from_renderer(h, h->r.ReadFramebuffer(host, bytes));
 }
+int spl_renderer_fence_copies(spl_renderer* h)
+{
+    if (!h) return set_error(SPL_ERR_ARG, "null argument");
+    return from_renderer(h, h->r.FenceCopies());
+}
 int spl_renderer_synchronize(spl_renderer* h)
 {
     if (!h) return set_error(SPL_ERR_ARG, "null argument");
@@ -192,7 +197,9 @@ struct spl_sorter
     int numSMs = 148;
     uint64_t capacity = 0;
     void* control = nullptr;  // n | tickets | histograms
-    uint32_t* status = nullptr;
+    unsigned long long* status = nullptr;
+    uint32_t generation = 0;
+    int keysPerThread = 16;
 };
 
 namespace
@@ -226,6 +233,7 @@ spl_sorter* spl_sorter_create(int device, uint64_t capacity)
         delete s;
         return nullptr;
     }
+    cudaMemset(s->status, 0, splat::sort_status_bytes(s->capacity, splat::kMaxSortPasses));  // look-back words start invalid
     return s;
 }
 void spl_sorter_destroy(spl_sorter* s)
@@ -250,7 +258,12 @@ int spl_sorter_sort(spl_sorter* s, void* d_keys_in, void* d_vals_in, void* d_key
     const uint32_t n32 = (uint32_t)n;
     SORTER_TRY(cudaMemcpyAsync(s->control, &n32, sizeof n32, cudaMemcpyHostToDevice, stream));
     uint32_t* ctl = static_cast<uint32_t*>(s->control);
-    splat::SortWorkspace ws{ctl + 64, s->status, ctl + 8, s->capacity};
+    if (((++s->generation) & 0xffffu) == 0)
+    {
+        SORTER_TRY(cudaMemsetAsync(s->status, 0, splat::sort_status_bytes(s->capacity, splat::kMaxSortPasses), stream));
+        ++s->generation;
+    }
+    splat::SortWorkspace ws{ctl + 64, s->status, ctl + 8, s->capacity, s->generation, s->keysPerThread};
     auto* kin = static_cast<unsigned long long*>(d_keys_in);
     auto* kout = static_cast<unsigned long long*>(d_keys_out);
     auto* vin = static_cast<uint32_t*>(d_vals_in);

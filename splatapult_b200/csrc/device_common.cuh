@@ -19,6 +19,7 @@ constexpr int kMaxSortPasses = 8;    // 64-bit key / 8
 constexpr int kSortThreads = 256;    // onesweep CTA
 constexpr int kSortKeysPerThread = 16;
 constexpr int kSortTileKeys = kSortThreads * kSortKeysPerThread;  // 4096 keys = 32 KiB staged by one bulk copy
+constexpr int kSortMinTileKeys = kSortThreads * 8;                // smallest tile variant (sizes the look-back array)
 
 // look-back status word: [31:30] flag, [29:0] count
 constexpr uint32_t kFlagAggregate = 1u << 30;

@@ -17,8 +17,9 @@ cudaError_t pack_cloud(const void* deviceAos, uint32_t n, uint32_t strideBytes, 
 
 // ---- project.cu
 uint32_t project_num_blocks(uint32_t n);
+// digit0Hist: 256 global counters that receive the histogram of the emitted keys' lowest digit (may be null)
 cudaError_t launch_project(const PackedCloud& cloud, const FrameConstants& fc, ProjRecord* rec, unsigned long long* keys, uint32_t* vals,
-                           FrameCounters* ctr, unsigned long long* scanState, uint32_t capacity, cudaStream_t stream);
+                           FrameCounters* ctr, unsigned long long* scanState, uint32_t capacity, uint32_t* digit0Hist, cudaStream_t stream);
 
 cudaError_t launch_project_bin(const PackedCloud& cloud, const FrameConstants& fc, ProjRecord* rec, uint4* side, uint32_t* tileCount,
                                FrameCounters* ctr, cudaStream_t stream);
@@ -35,10 +36,12 @@ cudaError_t launch_segment_sort(unsigned long long* pairs, unsigned long long* s
 // ---- radix_sort.cu : device-wide LSD radix sort of (u64 key, u32 value) pairs, 8-bit digits, onesweep style
 struct SortWorkspace
 {
-    uint32_t* histograms;  // [kMaxSortPasses][256] global digit counts
-    uint32_t* status;      // [passes][tiles][256] decoupled look-back words
-    uint32_t* tickets;     // [kMaxSortPasses] dynamic tile ids
-    uint64_t capacity;     // keys the status array was sized for
+    uint32_t* histograms;         // [kMaxSortPasses][256] global digit counts; row 0 filled by the producer, row p+1 by pass p
+    unsigned long long* status;   // [passes][tiles][256] decoupled look-back words {flag, generation, count}
+    uint32_t* tickets;            // [kMaxSortPasses] dynamic tile ids (zeroed per sort)
+    uint64_t capacity;            // keys the status array was sized for
+    uint32_t generation;          // distinguishes this sort's look-back words from stale ones (16 bits used)
+    int keysPerThread;            // 16 (4096-key tiles, 3 CTAs/SM) or 8 (2048-key tiles, 5 CTAs/SM)
 };
 size_t sort_status_bytes(uint64_t capacity, int passes);
 // keys/vals ping-pong between (A) and (B); passes = ceil((endBit-beginBit)/8); the sorted result is in A when

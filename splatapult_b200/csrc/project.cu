@@ -251,14 +251,16 @@ template <int SH_MODE>
 __global__ void __launch_bounds__(kProjThreads)
 k_project(const PackedCloud cloud, const __grid_constant__ FrameConstants fc, ProjRecord* __restrict__ rec,
           unsigned long long* __restrict__ keys, uint32_t* __restrict__ vals, FrameCounters* __restrict__ ctr,
-          unsigned long long* __restrict__ scanState, uint32_t capacity)
+          unsigned long long* __restrict__ scanState, uint32_t capacity, uint32_t* __restrict__ digit0Hist)
 {
     __shared__ uint32_t sBlockId;
     __shared__ uint32_t sWarpTotal[kProjThreads / 32];
     __shared__ unsigned long long sBlockBase;
+    __shared__ uint32_t sDigit0[kRadixSize];  // histogram of the emitted keys' lowest digit (saves the sorter a pass)
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid == 0) sBlockId = atomicAdd(&ctr->projectTicket, 1u);  // dynamic id: predecessors are resident or done
+    sDigit0[tid] = 0;
     __syncthreads();
     const uint32_t vbid = sBlockId;
     const uint32_t i = vbid * kProjThreads + tid;
@@ -330,6 +332,8 @@ k_project(const PackedCloud cloud, const __grid_constant__ FrameConstants fc, Pr
     const uint32_t cntE = fits ? count : 0u;
     if (!fits) atomicOr(&ctr->overflow, 1u);
     const uint32_t gOff = fits ? (uint32_t)gOff64 : 0u;
+    // all cntE keys of this gaussian share their low 32 bits: one weighted update covers them
+    if (cntE && digit0Hist) atomicAdd(&sDigit0[refKey & (kRadixSize - 1)], cntE);
 
     uint32_t inclE = cntE;
 #pragma unroll
@@ -372,6 +376,12 @@ k_project(const PackedCloud cloud, const __grid_constant__ FrameConstants fc, Pr
             keys[oOff + k] = ((unsigned long long)tile << 32) | oKey;
             vals[oOff + k] = oId;
         }
+    }
+    if (digit0Hist)
+    {
+        __syncthreads();
+        const uint32_t c = sDigit0[tid];
+        if (c) atomicAdd(digit0Hist + tid, c);
     }
 }
 
@@ -503,15 +513,15 @@ cudaError_t launch_bin_instances(const uint4* side, uint32_t n, int tilesX, uint
 }
 
 cudaError_t launch_project(const PackedCloud& cloud, const FrameConstants& fc, ProjRecord* rec, unsigned long long* keys, uint32_t* vals,
-                           FrameCounters* ctr, unsigned long long* scanState, uint32_t capacity, cudaStream_t stream)
+                           FrameCounters* ctr, unsigned long long* scanState, uint32_t capacity, uint32_t* digit0Hist, cudaStream_t stream)
 {
     const uint32_t blocks = project_num_blocks(cloud.n);
     if (blocks == 0) return cudaSuccess;
     switch (cloud.shMode)
     {
-    case 0: k_project<0><<<blocks, kProjThreads, 0, stream>>>(cloud, fc, rec, keys, vals, ctr, scanState, capacity); break;
-    case 1: k_project<1><<<blocks, kProjThreads, 0, stream>>>(cloud, fc, rec, keys, vals, ctr, scanState, capacity); break;
-    default: k_project<3><<<blocks, kProjThreads, 0, stream>>>(cloud, fc, rec, keys, vals, ctr, scanState, capacity); break;
+    case 0: k_project<0><<<blocks, kProjThreads, 0, stream>>>(cloud, fc, rec, keys, vals, ctr, scanState, capacity, digit0Hist); break;
+    case 1: k_project<1><<<blocks, kProjThreads, 0, stream>>>(cloud, fc, rec, keys, vals, ctr, scanState, capacity, digit0Hist); break;
+    default: k_project<3><<<blocks, kProjThreads, 0, stream>>>(cloud, fc, rec, keys, vals, ctr, scanState, capacity, digit0Hist); break;
     }
     return cudaGetLastError();
 }

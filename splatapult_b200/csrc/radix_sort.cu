@@ -7,13 +7,16 @@
 //
 // Differences in kind, not only in speed:
 //   * the reference re-reduces ALL workgroup histograms in EVERY workgroup (O(WG^2) reads) and only
-//     ceil(n/262144) of its workgroups see data; here every digit's global histogram is built once, up front,
-//     in one pass over the keys (S1), and each scatter pass (S2) resolves its tile's offsets with a
-//     decoupled look-back over per-tile status words: one read + one write of the data per pass.
-//   * key tiles (4096 keys = 32 KiB, + 16 KiB payload) are staged into shared memory by the TMA engine
-//     (cp.async.bulk + mbarrier, SASS UBLKCP) instead of per-thread loads; ranks come from warp match /
-//     popc ("warp-scan scatter"); the tile is reordered in shared memory so global stores are digit-run coalesced.
-//   * element counts are read from device memory: no host round trip anywhere.
+//     ceil(n/262144) of its workgroups see data.  Here each scatter pass (S2) resolves its tile's offsets with a
+//     decoupled look-back over per-tile status words: one read + one write of the data per pass;
+//   * digit histograms never cost a pass over the data: pass p accumulates the histogram of digit p+1 while the
+//     keys are in registers, and digit 0's comes from the producer (the projection kernel, weighted by each
+//     gaussian's tile count; k_sort_histogram for the stand-alone sorter);
+//   * key tiles are staged into shared memory by the TMA engine (cp.async.bulk + mbarrier, SASS UBLKCP) instead
+//     of per-thread loads; ranks come from warp match / popc ("warp-scan scatter"); the tile is reordered in
+//     shared memory so global stores are digit-run coalesced;
+//   * look-back words carry a 16-bit generation, so nothing is cleared between sorts; element counts are read
+//     from device memory: no host round trip anywhere.
 #include "device_common.cuh"
 #include "kernels.h"
 
@@ -21,39 +24,41 @@ namespace splat
 {
 
 constexpr int kHistThreads = 256;
-constexpr int kWarpsPerSortCta = kSortThreads / 32;
 
 __device__ __forceinline__ uint32_t digit_of(unsigned long long key, int shift, uint32_t mask) { return (uint32_t)(key >> shift) & mask; }
-__host__ __device__ __forceinline__ uint32_t digit_mask(int shift, int endBit) { const int bits = endBit - shift; return bits >= kRadixBits ? (uint32_t)(kRadixSize - 1) : ((1u << bits) - 1u); }
+__host__ __device__ __forceinline__ uint32_t digit_mask(int shift, int endBit)
+{
+    const int bits = endBit - shift;
+    return bits >= kRadixBits ? (uint32_t)(kRadixSize - 1) : ((1u << bits) - 1u);
+}
+
+// look-back status word: [63:62] flag, [47:32] generation, [31:0] count
+constexpr unsigned long long kStAggregate = 1ull << 62;
+constexpr unsigned long long kStPrefix = 2ull << 62;
+__device__ __forceinline__ unsigned long long st_pack(unsigned long long flag, uint32_t gen, uint32_t count)
+{
+    return flag | ((unsigned long long)(gen & 0xffffu) << 32) | count;
+}
+__device__ __forceinline__ bool st_valid(unsigned long long w, uint32_t gen) { return (w >> 62) != 0 && (uint32_t)((w >> 32) & 0xffffu) == (gen & 0xffffu); }
 
 // ---------------------------------------------------------------------------------------------------
-// S1: all digit histograms in one pass; also clears the look-back status words this sort will use
+// S1 (stand-alone sorter only): histogram of the FIRST digit; TMA-staged, double-buffered
 // ---------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kHistThreads)
-k_sort_histogram(const unsigned long long* __restrict__ keys, const uint32_t* __restrict__ nDevice, int beginBit, int endBit, int passes,
-                 uint32_t* __restrict__ histograms, uint32_t* __restrict__ status, uint32_t maxTiles)
+k_sort_histogram(const unsigned long long* __restrict__ keys, const uint32_t* __restrict__ nDevice, int shift, uint32_t mask,
+                 uint32_t* __restrict__ histogram)
 {
     extern __shared__ __align__(128) unsigned char smemRaw[];
     unsigned long long* sKeys[2] = {reinterpret_cast<unsigned long long*>(smemRaw),
                                     reinterpret_cast<unsigned long long*>(smemRaw) + kSortTileKeys};
-    uint32_t* sHist = reinterpret_cast<uint32_t*>(smemRaw + 2 * kSortTileKeys * sizeof(unsigned long long));  // [passes][256]
+    __shared__ uint32_t sHist[kRadixSize];
     __shared__ __align__(8) uint64_t sBar[2];
 
     const int tid = threadIdx.x;
     const uint32_t n = *nDevice;
     const uint32_t numTiles = (n + kSortTileKeys - 1) / kSortTileKeys;
 
-    // clear status rows [pass][0..numTiles) x 256
-    {
-        const uint32_t wordsPerPass = numTiles * kRadixSize;
-        for (int p = 0; p < passes; p++)
-        {
-            uint4* row = reinterpret_cast<uint4*>(status + (size_t)p * maxTiles * kRadixSize);
-            for (uint32_t w = blockIdx.x * kHistThreads + tid; w < wordsPerPass / 4; w += gridDim.x * kHistThreads) row[w] = make_uint4(0, 0, 0, 0);
-        }
-    }
-
-    for (int k = tid; k < passes * kRadixSize; k += kHistThreads) sHist[k] = 0;
+    sHist[tid] = 0;
     if (tid == 0)
     {
         mbar_init(&sBar[0], 1);
@@ -81,65 +86,56 @@ k_sort_histogram(const unsigned long long* __restrict__ keys, const uint32_t* __
         phase[buf] ^= 1;
         const uint32_t cnt = min((uint32_t)kSortTileKeys, n - tile * kSortTileKeys);
 #pragma unroll 4
-        for (int k = 0; k < kSortKeysPerThread; k++)
+        for (int k = 0; k < kSortTileKeys / kHistThreads; k++)
         {
             const uint32_t idx = k * kHistThreads + tid;
-            const bool ok = idx < cnt;
-            const unsigned long long key = ok ? sKeys[buf][idx] : 0ull;
-            const uint32_t active = __ballot_sync(0xffffffffu, ok);
-            for (int p = 0; p < passes; p++)
-            {
-                const int sh = beginBit + p * kRadixBits;
-                const uint32_t d = digit_of(key, sh, digit_mask(sh, endBit));
-                if (p < 3)
-                {
-                    if (ok) atomicAdd(&sHist[p * kRadixSize + d], 1u);
-                }
-                else if (ok)
-                {
-                    // high digits (top depth byte, tile id) are nearly constant across a warp: aggregate
-                    const uint32_t peers = __match_any_sync(active, d);
-                    if ((peers & lanemask_lt()) == 0) atomicAdd(&sHist[p * kRadixSize + d], (uint32_t)__popc(peers));
-                }
-            }
+            if (idx < cnt) atomicAdd(&sHist[digit_of(sKeys[buf][idx], shift, mask)], 1u);
         }
         __syncthreads();  // all reads of sKeys[buf] done before it is refilled two tiles from now
         buf ^= 1;
     }
     __syncthreads();
-    for (int k = tid; k < passes * kRadixSize; k += kHistThreads)
-    {
-        const uint32_t c = sHist[k];
-        if (c) atomicAdd(&histograms[k], c);
-    }
+    const uint32_t c = sHist[tid];
+    if (c) atomicAdd(&histogram[tid], c);
 }
 
 // ---------------------------------------------------------------------------------------------------
-// S2: one scatter pass (onesweep): rank in tile, look back for the tile's global digit offsets, scatter
+// S2: one scatter pass (onesweep): rank in tile, look back for the tile's global digit offsets, scatter;
+//     also accumulates the NEXT pass's digit histogram
 // ---------------------------------------------------------------------------------------------------
+template <int KPT>
 struct SortSmem
 {
-    unsigned long long keys[kSortTileKeys];           // TMA destination; reused for the digit-ordered tile
-    uint32_t vals[kSortTileKeys];                     // TMA destination; reused for the digit-ordered payloads
-    uint32_t warpCount[kWarpsPerSortCta][kRadixSize]; // per-warp digit counters -> exclusive prefix over warps
-    uint32_t ctaExcl[kRadixSize];                     // first local slot of each digit
-    uint32_t globalBase[kRadixSize];                  // global index of local slot 0 of each digit (minus ctaExcl)
-    uint32_t scanTmp[kWarpsPerSortCta];
+    static constexpr int kTile = kSortThreads * KPT;
+    static constexpr int kWarps = kSortThreads / 32;
+    unsigned long long keys[kTile];               // TMA destination; reused for the digit-ordered tile
+    uint32_t vals[kTile];                         // TMA destination; reused for the digit-ordered payloads
+    uint32_t warpCount[kWarps][kRadixSize];       // per-warp digit counters -> exclusive prefix over warps
+    uint32_t ctaExcl[kRadixSize];                 // first local slot of each digit
+    uint32_t globalBase[kRadixSize];              // global index of local slot 0 of each digit (minus ctaExcl)
+    uint32_t nextHist[kRadixSize];                // histogram of the next pass's digit over this CTA's tiles
+    uint32_t scanTmp[kWarps];
     uint32_t tile;
     uint64_t bar;
 };
 
-__global__ void __launch_bounds__(kSortThreads, 3)
+template <int KPT>
+__global__ void __launch_bounds__(kSortThreads, KPT == 16 ? 3 : 5)
 k_sort_onesweep(const unsigned long long* __restrict__ keysIn, const uint32_t* __restrict__ valsIn, unsigned long long* __restrict__ keysOut,
-                uint32_t* __restrict__ valsOut, const uint32_t* __restrict__ nDevice, int shift, uint32_t mask, const uint32_t* __restrict__ histogram,
-                uint32_t* __restrict__ status, uint32_t* __restrict__ ticket)
+                uint32_t* __restrict__ valsOut, const uint32_t* __restrict__ nDevice, int shift, uint32_t mask, int nextShift, uint32_t nextMask,
+                const uint32_t* __restrict__ histogram, uint32_t* __restrict__ histogramNext, unsigned long long* __restrict__ status,
+                uint32_t* __restrict__ ticket, uint32_t gen)
 {
+    using Smem = SortSmem<KPT>;
+    constexpr int kTile = Smem::kTile;
+    constexpr int kWarps = Smem::kWarps;
     extern __shared__ __align__(128) unsigned char smemRaw[];
-    SortSmem& s = *reinterpret_cast<SortSmem*>(smemRaw);
+    Smem& s = *reinterpret_cast<Smem*>(smemRaw);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t n = *nDevice;
-    const uint32_t numTiles = (n + kSortTileKeys - 1) / kSortTileKeys;
+    const uint32_t numTiles = (n + kTile - 1) / kTile;
+    const bool wantNext = histogramNext != nullptr;
 
     // global exclusive scan of this pass's digit histogram: thread d owns digit d
     uint32_t digitStart;
@@ -153,6 +149,7 @@ k_sort_onesweep(const unsigned long long* __restrict__ keysIn, const uint32_t* _
             if (lane >= d) incl += v;
         }
         if (lane == 31) s.scanTmp[warp] = incl;
+        s.nextHist[tid] = 0;
         if (tid == 0)
         {
             mbar_init(&s.bar, 1);
@@ -161,7 +158,7 @@ k_sort_onesweep(const unsigned long long* __restrict__ keysIn, const uint32_t* _
         __syncthreads();
         uint32_t base = 0;
 #pragma unroll
-        for (int w = 0; w < kWarpsPerSortCta; w++)
+        for (int w = 0; w < kWarps; w++)
             if (w < warp) base += s.scanTmp[w];
         digitStart = base + incl - h;
         __syncthreads();
@@ -171,36 +168,35 @@ k_sort_onesweep(const unsigned long long* __restrict__ keysIn, const uint32_t* _
     for (;;)
     {
         if (tid == 0) s.tile = atomicAdd(ticket, 1u);
-        // clear per-warp counters for this tile
 #pragma unroll
-        for (int w = 0; w < kWarpsPerSortCta; w++) s.warpCount[w][tid] = 0;
+        for (int w = 0; w < kWarps; w++) s.warpCount[w][tid] = 0;
         __syncthreads();
         const uint32_t tile = s.tile;
         if (tile >= numTiles) break;
-        const uint32_t nValid = min((uint32_t)kSortTileKeys, n - tile * kSortTileKeys);
+        const uint32_t nValid = min((uint32_t)kTile, n - tile * kTile);
 
         if (tid == 0)
         {
             const uint32_t kb = (nValid * 8u + 15u) & ~15u, vb = (nValid * 4u + 15u) & ~15u;
             fence_proxy_async();
             mbar_expect_tx(&s.bar, kb + vb);
-            bulk_g2s(s.keys, keysIn + (size_t)tile * kSortTileKeys, kb, &s.bar);
-            bulk_g2s(s.vals, valsIn + (size_t)tile * kSortTileKeys, vb, &s.bar);
+            bulk_g2s(s.keys, keysIn + (size_t)tile * kTile, kb, &s.bar);
+            bulk_g2s(s.vals, valsIn + (size_t)tile * kTile, vb, &s.bar);
         }
         mbar_wait(&s.bar, parity);
         parity ^= 1;
 
-        // ---- rank: warp w owns items [w*512, (w+1)*512), item j of a lane = w*512 + j*32 + lane (memory order)
-        unsigned long long key[kSortKeysPerThread];
-        uint16_t pos[kSortKeysPerThread];
+        // ---- rank: warp w owns items [w*KPT*32, (w+1)*KPT*32), item j of a lane = base + j*32 + lane (memory order)
+        unsigned long long key[KPT];
+        uint16_t pos[KPT];
 #pragma unroll
-        for (int j = 0; j < kSortKeysPerThread; j++)
+        for (int j = 0; j < KPT; j++)
         {
-            const uint32_t idx = warp * (kSortKeysPerThread * 32) + j * 32 + lane;
+            const uint32_t idx = warp * (KPT * 32) + j * 32 + lane;
             key[j] = idx < nValid ? s.keys[idx] : ~0ull;  // padding sorts last inside the tile and is never written
         }
 #pragma unroll
-        for (int j = 0; j < kSortKeysPerThread; j++)
+        for (int j = 0; j < KPT; j++)
         {
             const uint32_t d = digit_of(key[j], shift, mask);
             const uint32_t peers = __match_any_sync(0xffffffffu, d);
@@ -211,23 +207,32 @@ k_sort_onesweep(const unsigned long long* __restrict__ keysIn, const uint32_t* _
             __syncwarp();
             pos[j] = (uint16_t)(prev + before);
         }
+        if (wantNext)
+        {
+            // next pass's digit histogram, while the keys are in registers (shared-memory atomics)
+#pragma unroll
+            for (int j = 0; j < KPT; j++)
+            {
+                const uint32_t idx = warp * (KPT * 32) + j * 32 + lane;
+                if (idx < nValid) atomicAdd(&s.nextHist[digit_of(key[j], nextShift, nextMask)], 1u);
+            }
+        }
         __syncthreads();
 
         // ---- per-digit totals (thread d), publish, look back, local/global bases
         {
             uint32_t run = 0;
 #pragma unroll
-            for (int w = 0; w < kWarpsPerSortCta; w++)
+            for (int w = 0; w < kWarps; w++)
             {
                 const uint32_t c = s.warpCount[w][tid];
                 s.warpCount[w][tid] = run;
                 run += c;
             }
             const uint32_t cnt = run;
-            uint32_t* myStatus = status + (size_t)tile * kRadixSize + tid;
-            st_relaxed_u32(myStatus, (tile == 0 ? kFlagPrefix : kFlagAggregate) | cnt);
+            unsigned long long* myStatus = status + (size_t)tile * kRadixSize + tid;
+            st_relaxed_u64(myStatus, st_pack(tile == 0 ? kStPrefix : kStAggregate, gen, cnt));
 
-            // exclusive scan of cnt over the 256 digits
             uint32_t incl = cnt;
 #pragma unroll
             for (int d = 1; d < 32; d <<= 1)
@@ -239,43 +244,60 @@ k_sort_onesweep(const unsigned long long* __restrict__ keysIn, const uint32_t* _
             __syncthreads();
             uint32_t base = 0;
 #pragma unroll
-            for (int w = 0; w < kWarpsPerSortCta; w++)
+            for (int w = 0; w < kWarps; w++)
                 if (w < warp) base += s.scanTmp[w];
             const uint32_t excl = base + incl - cnt;
 
             uint32_t prior = 0;
             if (tile > 0)
             {
-                for (int t = (int)tile - 1; t >= 0; t--)
+                // windowed look-back: kLookWindow predecessors are polled with independent loads in flight, so
+                // the walk costs one L2 round trip per window instead of one per tile
+                constexpr int kLookWindow = 8;
+                int t = (int)tile - 1;
+                bool done = false;
+                while (!done)
                 {
-                    const uint32_t* st = status + (size_t)t * kRadixSize + tid;
-                    uint32_t v;
-                    do { v = ld_relaxed_u32(st); } while ((v & kFlagMask) == 0);
-                    prior += v & kValueMask;
-                    if ((v & kFlagMask) == kFlagPrefix) break;
+                    unsigned long long v[kLookWindow];
+#pragma unroll
+                    for (int i = 0; i < kLookWindow; i++)
+                        v[i] = (t - i >= 0) ? ld_relaxed_u64(status + (size_t)(t - i) * kRadixSize + tid) : st_pack(kStPrefix, gen, 0u);
+                    int used = 0;
+#pragma unroll
+                    for (int i = 0; i < kLookWindow; i++)
+                    {
+                        if (!done && used == i)
+                        {
+                            if (st_valid(v[i], gen))
+                            {
+                                prior += (uint32_t)v[i];
+                                used = i + 1;
+                                done = (v[i] >> 62) == 2;
+                            }
+                        }
+                    }
+                    t -= used;  // re-poll from the first word that was not yet published
                 }
-                st_relaxed_u32(myStatus, kFlagPrefix | (prior + cnt));
+                st_relaxed_u64(myStatus, st_pack(kStPrefix, gen, prior + cnt));
             }
             s.ctaExcl[tid] = excl;
             s.globalBase[tid] = digitStart + prior - excl;
         }
         __syncthreads();
 
-        // ---- reorder the tile in shared memory: keys
+        // ---- reorder the tile in shared memory
 #pragma unroll
-        for (int j = 0; j < kSortKeysPerThread; j++)
+        for (int j = 0; j < KPT; j++)
         {
             const uint32_t d = digit_of(key[j], shift, mask);
-            const uint32_t lp = s.ctaExcl[d] + s.warpCount[warp][d] + pos[j];
-            pos[j] = (uint16_t)lp;
+            pos[j] = (uint16_t)(s.ctaExcl[d] + s.warpCount[warp][d] + pos[j]);
         }
-        // payloads: staged (memory order) -> registers, then both to their sorted slots
-        uint32_t val[kSortKeysPerThread];
+        uint32_t val[KPT];
 #pragma unroll
-        for (int j = 0; j < kSortKeysPerThread; j++) val[j] = s.vals[warp * (kSortKeysPerThread * 32) + j * 32 + lane];
+        for (int j = 0; j < KPT; j++) val[j] = s.vals[warp * (KPT * 32) + j * 32 + lane];
         __syncthreads();  // every staged key/payload is in registers
 #pragma unroll
-        for (int j = 0; j < kSortKeysPerThread; j++)
+        for (int j = 0; j < KPT; j++)
         {
             s.keys[pos[j]] = key[j];
             s.vals[pos[j]] = val[j];
@@ -284,7 +306,7 @@ k_sort_onesweep(const unsigned long long* __restrict__ keysIn, const uint32_t* _
 
         // ---- coalesced scatter: slot i of digit d goes to globalBase[d] + i
 #pragma unroll 4
-        for (int k = 0; k < kSortKeysPerThread; k++)
+        for (int k = 0; k < KPT; k++)
         {
             const uint32_t i = k * kSortThreads + tid;
             if (i < nValid)
@@ -297,43 +319,71 @@ k_sort_onesweep(const unsigned long long* __restrict__ keysIn, const uint32_t* _
         }
         __syncthreads();  // shared tile fully consumed before the next bulk copy lands
     }
+    if (wantNext)
+    {
+        const uint32_t c = s.nextHist[tid];
+        if (c) atomicAdd(&histogramNext[tid], c);
+    }
 }
 
 size_t sort_status_bytes(uint64_t capacity, int passes)
 {
-    const uint64_t maxTiles = (capacity + kSortTileKeys - 1) / kSortTileKeys + 1;
-    return (size_t)passes * maxTiles * kRadixSize * sizeof(uint32_t);
+    const uint64_t maxTiles = (capacity + kSortMinTileKeys - 1) / kSortMinTileKeys + 1;
+    return (size_t)passes * maxTiles * kRadixSize * sizeof(unsigned long long);
 }
 
-static cudaError_t ensure_sort_attrs(size_t histSmem, size_t sortSmem)
+template <int KPT>
+static cudaError_t launch_passes_t(unsigned long long* keysA, uint32_t* valsA, unsigned long long* keysB, uint32_t* valsB, const uint32_t* nDevice,
+                                   uint64_t capacity, int beginBit, int endBit, const SortWorkspace& ws, int numSMs, cudaStream_t stream)
 {
+    using Smem = SortSmem<KPT>;
     static bool attrSet[64] = {};
     int dev = 0;
     cudaGetDevice(&dev);
     if (!attrSet[dev & 63])
     {
-        cudaError_t e = cudaFuncSetAttribute(k_sort_histogram, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)histSmem);
-        if (e != cudaSuccess) return e;
-        e = cudaFuncSetAttribute(k_sort_onesweep, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sortSmem);
+        cudaError_t e = cudaFuncSetAttribute(k_sort_onesweep<KPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem));
         if (e != cudaSuccess) return e;
         attrSet[dev & 63] = true;
     }
-    return cudaSuccess;
+    const int passes = (endBit - beginBit + kRadixBits - 1) / kRadixBits;
+    const uint64_t maxTiles = (capacity + kSortMinTileKeys - 1) / kSortMinTileKeys + 1;
+    const uint32_t capTiles = (uint32_t)((capacity + Smem::kTile - 1) / Smem::kTile);
+    const uint32_t ctasPerSM = KPT == 16 ? 3u : 5u;
+    const uint32_t grid = max(1u, min((uint32_t)numSMs * ctasPerSM, capTiles));
+    for (int p = 0; p < passes; p++)
+    {
+        const unsigned long long* kin = (p & 1) ? keysB : keysA;
+        const uint32_t* vin = (p & 1) ? valsB : valsA;
+        unsigned long long* kout = (p & 1) ? keysA : keysB;
+        uint32_t* vout = (p & 1) ? valsA : valsB;
+        const int shift = beginBit + p * kRadixBits;
+        const bool last = p == passes - 1;
+        const int nshift = last ? 0 : shift + kRadixBits;
+        k_sort_onesweep<KPT><<<grid, kSortThreads, sizeof(Smem), stream>>>(
+            kin, vin, kout, vout, nDevice, shift, digit_mask(shift, endBit), nshift, last ? 0u : digit_mask(nshift, endBit),
+            ws.histograms + p * kRadixSize, last ? nullptr : ws.histograms + (p + 1) * kRadixSize,
+            ws.status + (size_t)p * maxTiles * kRadixSize, ws.tickets + p, ws.generation);
+    }
+    return cudaGetLastError();
 }
-
-static constexpr size_t kHistSmemBytes = 2 * kSortTileKeys * sizeof(unsigned long long) + (size_t)kMaxSortPasses * kRadixSize * sizeof(uint32_t);
 
 cudaError_t launch_sort_histogram(const unsigned long long* keysA, const uint32_t* nDevice, uint64_t capacity, int beginBit, int endBit,
                                   const SortWorkspace& ws, int numSMs, cudaStream_t stream)
 {
-    const int passes = (endBit - beginBit + kRadixBits - 1) / kRadixBits;
-    if (passes < 1 || passes > kMaxSortPasses) return cudaErrorInvalidValue;
-    cudaError_t e = ensure_sort_attrs(kHistSmemBytes, sizeof(SortSmem));
-    if (e != cudaSuccess) return e;
-    const uint32_t maxTiles = (uint32_t)((capacity + kSortTileKeys - 1) / kSortTileKeys + 1);
+    static bool attrSet[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    const size_t smem = 2 * kSortTileKeys * sizeof(unsigned long long);
+    if (!attrSet[dev & 63])
+    {
+        cudaError_t e = cudaFuncSetAttribute(k_sort_histogram, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        attrSet[dev & 63] = true;
+    }
     const uint32_t capTiles = (uint32_t)((capacity + kSortTileKeys - 1) / kSortTileKeys);
-    const uint32_t histGrid = max(1u, min((uint32_t)numSMs * 3u, capTiles));
-    k_sort_histogram<<<histGrid, kHistThreads, kHistSmemBytes, stream>>>(keysA, nDevice, beginBit, endBit, passes, ws.histograms, ws.status, maxTiles);
+    const uint32_t grid = max(1u, min((uint32_t)numSMs * 3u, capTiles));
+    k_sort_histogram<<<grid, kHistThreads, smem, stream>>>(keysA, nDevice, beginBit, digit_mask(beginBit, endBit), ws.histograms);
     return cudaGetLastError();
 }
 
@@ -342,23 +392,8 @@ cudaError_t launch_sort_passes(unsigned long long* keysA, uint32_t* valsA, unsig
 {
     const int passes = (endBit - beginBit + kRadixBits - 1) / kRadixBits;
     if (passes < 1 || passes > kMaxSortPasses) return cudaErrorInvalidValue;
-    cudaError_t e = ensure_sort_attrs(kHistSmemBytes, sizeof(SortSmem));
-    if (e != cudaSuccess) return e;
-    const uint32_t maxTiles = (uint32_t)((capacity + kSortTileKeys - 1) / kSortTileKeys + 1);
-    const uint32_t capTiles = (uint32_t)((capacity + kSortTileKeys - 1) / kSortTileKeys);
-    const uint32_t sortGrid = max(1u, min((uint32_t)numSMs * 3u, capTiles));
-    for (int p = 0; p < passes; p++)
-    {
-        const unsigned long long* kin = (p & 1) ? keysB : keysA;
-        const uint32_t* vin = (p & 1) ? valsB : valsA;
-        unsigned long long* kout = (p & 1) ? keysA : keysB;
-        uint32_t* vout = (p & 1) ? valsA : valsB;
-        const int shift = beginBit + p * kRadixBits;
-        k_sort_onesweep<<<sortGrid, kSortThreads, sizeof(SortSmem), stream>>>(kin, vin, kout, vout, nDevice, shift, digit_mask(shift, endBit),
-                                                                              ws.histograms + p * kRadixSize,
-                                                                              ws.status + (size_t)p * maxTiles * kRadixSize, ws.tickets + p);
-    }
-    return cudaGetLastError();
+    if (ws.keysPerThread == 8) return launch_passes_t<8>(keysA, valsA, keysB, valsB, nDevice, capacity, beginBit, endBit, ws, numSMs, stream);
+    return launch_passes_t<16>(keysA, valsA, keysB, valsB, nDevice, capacity, beginBit, endBit, ws, numSMs, stream);
 }
 
 cudaError_t launch_radix_sort(unsigned long long* keysA, uint32_t* valsA, unsigned long long* keysB, uint32_t* valsB, const uint32_t* nDevice,

@@ -57,12 +57,19 @@ struct RendererImpl
     FrameCounters* dCtr = nullptr;
     uint32_t* dHist = nullptr;
     unsigned long long* dScan = nullptr;
-    uint32_t* dStatus = nullptr;
+    unsigned long long* dStatus = nullptr;
+    uint32_t sortGeneration = 0;
+    int sortKpt = 16;
     uint2* dRanges = nullptr;
     uint32_t* dTileCtl = nullptr;  // tileCount | tileCursor | largeList, rangesTiles words each
     uint4* dSide = nullptr;        // per-gaussian {rect, depthKey, count} of the binned sort
     uint32_t rangesTiles = 0;
-    void* dFb = nullptr;
+    void* dFb = nullptr;             // target of the last Render (= dFbs[fbCur])
+    void* dFbs[2] = {nullptr, nullptr};
+    int fbNext = 0, fbCur = 0;
+    cudaStream_t copyStream = nullptr;  // framebuffer D->H copies overlap the next frame
+    cudaEvent_t evRendered[2] = {}, evCopied[2] = {};
+    bool copyPending[2] = {false, false};
     size_t fbBytes = 0;
     int fbW = 0, fbH = 0;
 
@@ -104,9 +111,16 @@ struct RendererImpl
         if (!initialized && !stream && !dFb) return;
         cudaSetDevice(device);
         if (stream) cudaStreamSynchronize(stream);
+        if (copyStream)
+        {
+            cudaStreamSynchronize(copyStream);
+            for (int k = 0; k < 2; k++) { cudaEventDestroy(evRendered[k]); cudaEventDestroy(evCopied[k]); }
+            cudaStreamDestroy(copyStream);
+            copyStream = nullptr;
+        }
         freeFrameBuffers();
-        cudaFree(dPlanes); cudaFree(dRec); cudaFree(dControl); cudaFree(dRanges); cudaFree(dFb); cudaFree(dTileCtl); cudaFree(dSide);
-        dPlanes = nullptr; dRec = nullptr; dControl = nullptr; dRanges = nullptr; dFb = nullptr; dTileCtl = nullptr; dSide = nullptr;
+        cudaFree(dPlanes); cudaFree(dRec); cudaFree(dControl); cudaFree(dRanges); cudaFree(dFbs[0]); cudaFree(dFbs[1]); cudaFree(dTileCtl); cudaFree(dSide);
+        dPlanes = nullptr; dRec = nullptr; dControl = nullptr; dRanges = nullptr; dFb = dFbs[0] = dFbs[1] = nullptr; dTileCtl = nullptr; dSide = nullptr;
         if (evCreated)
             for (auto& e : ev) cudaEventDestroy(e);
         evCreated = false;
@@ -140,6 +154,8 @@ struct RendererImpl
         CU_TRY(cudaMalloc(&dValsA, padded * 4));
         CU_TRY(cudaMalloc(&dValsB, padded * 4));
         CU_TRY(cudaMalloc(&dStatus, sort_status_bytes(want, kMaxSortPasses)));
+        CU_TRY(cudaMemsetAsync(dStatus, 0, sort_status_bytes(want, kMaxSortPasses), stream));
+        sortGeneration = 0;
         // the padding is read (never used) by the last tile's bulk copy: keep it defined
         CU_TRY(cudaMemsetAsync(dKeysA, 0, padded * 8, stream));
         CU_TRY(cudaMemsetAsync(dKeysB, 0, padded * 8, stream));
@@ -280,14 +296,20 @@ struct RendererImpl
         else
         {
             // LSD: device-wide onesweep radix sort of the packed u64 keys, then boundary detection
-            CU_TRY(launch_project(cloud, fc, dRec, dKeysA, dValsA, dCtr, dScan, (uint32_t)capacity, stream));
+            // look-back words are generation-tagged instead of cleared; re-zero only when the 16-bit tag wraps
+            if (((++sortGeneration) & 0xffffu) == 0)
+            {
+                CU_TRY(cudaMemsetAsync(dStatus, 0, sort_status_bytes(capacity, kMaxSortPasses), stream));
+                ++sortGeneration;
+            }
+            // the projection kernel also produces the first digit's histogram; pass p produces pass p+1's
+            CU_TRY(launch_project(cloud, fc, dRec, dKeysA, dValsA, dCtr, dScan, (uint32_t)capacity, dHist, stream));
             launches += n ? 1 : 0;
             if (profile) CU_TRY(cudaEventRecord(ev[1], stream));
-            SortWorkspace ws{dHist, dStatus, dCtr->sortTickets, capacity};
-            CU_TRY(launch_sort_histogram(dKeysA, &dCtr->usedInstances, capacity, 0, sortBits, ws, numSMs, stream));
             if (profile) CU_TRY(cudaEventRecord(ev[6], stream));
+            SortWorkspace ws{dHist, dStatus, dCtr->sortTickets, capacity, sortGeneration, sortKpt};
             CU_TRY(launch_sort_passes(dKeysA, dValsA, dKeysB, dValsB, &dCtr->usedInstances, capacity, 0, sortBits, ws, numSMs, stream));
-            launches += 1 + sortPasses;
+            launches += sortPasses;
             if (profile) CU_TRY(cudaEventRecord(ev[2], stream));
             CU_TRY(launch_tile_ranges(sortedKeys(), &dCtr->usedInstances, capacity, dRanges, numTiles, numSMs, stream));
             launches += 1;
@@ -313,18 +335,52 @@ struct RendererImpl
         if (need > fbBytes)
         {
             CU_TRY(cudaStreamSynchronize(stream));
-            cudaFree(dFb);
-            dFb = nullptr;
-            CU_TRY(cudaMalloc(&dFb, need));
+            if (copyStream) CU_TRY(cudaStreamSynchronize(copyStream));
+            for (int k = 0; k < 2; k++)
+            {
+                cudaFree(dFbs[k]);
+                dFbs[k] = nullptr;
+                CU_TRY(cudaMalloc(&dFbs[k], need));
+                copyPending[k] = false;
+            }
             fbBytes = need;
         }
+        if (!copyStream)
+        {
+            CU_TRY(cudaStreamCreateWithFlags(&copyStream, cudaStreamNonBlocking));
+            for (int k = 0; k < 2; k++)
+            {
+                CU_TRY(cudaEventCreateWithFlags(&evRendered[k], cudaEventDisableTiming));
+                CU_TRY(cudaEventCreateWithFlags(&evCopied[k], cudaEventDisableTiming));
+            }
+        }
+        // two render targets: frame k+1 is composited while frame k is still being copied to the host
+        const int target = fbNext;
+        fbNext ^= 1;
+        if (copyPending[target])
+        {
+            CU_TRY(cudaStreamWaitEvent(stream, evCopied[target], 0));  // the copy that last read this target must be done
+            copyPending[target] = false;
+        }
+        dFb = dFbs[target];
+        fbCur = target;
         fbW = fc.width; fbH = fc.height;
         if (profile) CU_TRY(cudaEventRecord(ev[4], stream));
         const bool binned = frameSortMode == SPL_SORT_BINNED;
         CU_TRY(launch_composite(dRanges, binned ? reinterpret_cast<const uint32_t*>(dKeysA) : sortedVals(), binned ? 2 : 1, dRec, dFb, fbFormat, fc.width, fc.height, fc.tilesX, fc.tilesY, (float)earlyOutT, stream));
         launches += 1;
         if (profile) CU_TRY(cudaEventRecord(ev[5], stream));
+        CU_TRY(cudaEventRecord(evRendered[target], stream));
         haveRender = true;
+        return ok();
+    }
+
+    // enqueue (on the render stream) a wait for every framebuffer copy still in flight on the copy stream
+    int fenceCopies()
+    {
+        if (int rc = begin()) return rc;
+        for (int k = 0; k < 2; k++)
+            if (copyPending[k]) CU_TRY(cudaStreamWaitEvent(stream, evCopied[k], 0));
         return ok();
     }
 
@@ -356,8 +412,13 @@ struct RendererImpl
                 if (int rc = render(a, a + 16, a + 32, a + 36)) return rc;
             }
         }
-        CU_TRY(cudaMemcpyAsync(host, dFb, need, cudaMemcpyDeviceToHost, stream));
-        if (wait) CU_TRY(cudaStreamSynchronize(stream));
+        // device -> host on the copy stream, ordered after the composite of this target by an event; the next
+        // Render writes the other target, so it overlaps this copy
+        CU_TRY(cudaStreamWaitEvent(copyStream, evRendered[fbCur], 0));
+        CU_TRY(cudaMemcpyAsync(host, dFb, need, cudaMemcpyDeviceToHost, copyStream));
+        CU_TRY(cudaEventRecord(evCopied[fbCur], copyStream));
+        copyPending[fbCur] = true;
+        if (wait) CU_TRY(cudaStreamSynchronize(copyStream));
         return ok();
     }
 
@@ -506,10 +567,13 @@ bool SplatRenderer::Synchronize()
 {
     if (int rc = impl->begin()) { status = rc; error = impl->error; return false; }
     cudaError_t e = cudaStreamSynchronize(impl->stream);
+    if (e == cudaSuccess && impl->copyStream) e = cudaStreamSynchronize(impl->copyStream);
     if (e != cudaSuccess) { status = impl->fail(SPL_ERR_CUDA, std::string("cudaStreamSynchronize: ") + cudaGetErrorString(e)); error = impl->error; return false; }
     status = 0;
     return true;
 }
+
+bool SplatRenderer::FenceCopies() { FORWARD(impl->fenceCopies()); }
 
 bool SplatRenderer::GetStats(spl_stats* out) { FORWARD(impl->stats(out)); }
 
@@ -526,6 +590,10 @@ bool SplatRenderer::SetOption(int option, double value)
     case SPL_OPT_EARLY_OUT_T: impl->earlyOutT = value; break;
     case SPL_OPT_PROFILE: impl->profile = value != 0.0; break;
     case SPL_OPT_INSTANCES_PER_GAUSSIAN: impl->instancesPerGaussian = value; break;
+    case SPL_OPT_SORT_TILE:
+        if (value != 2048 && value != 4096) { status = SPL_ERR_ARG; error = "sort tile must be 2048 or 4096 keys"; return false; }
+        impl->sortKpt = value == 2048 ? 8 : 16;
+        break;
     case SPL_OPT_SORT_MODE:
         if (value != SPL_SORT_BINNED && value != SPL_SORT_LSD) { status = SPL_ERR_ARG; error = "unknown sort mode"; return false; }
         impl->sortMode = (int)value;

@@ -329,3 +329,20 @@ def test_dense_tile_segments(splat, oracle, scratch, n, expect_path):
     _check_image(fb, want)
     r.SetOption(api.OPT_EARLY_OUT_T, 0.0)
     _check_image(_frame(r, cam, proj, 64, 64), want, exact_mode=True)
+
+
+def test_sort_tile_variants_give_identical_lists(splat, golden_dir):
+    """the onesweep sorter's two tile sizes (4096 / 2048 keys per CTA) are the same stable sort"""
+    if SORT_MODE != api.SORT_LSD:
+        pytest.skip("LSD path only")
+    g = np.load(os.path.join(golden_dir, "synth_2k_deg3_320x180.npz"))
+    out = []
+    for tile in (4096, 2048):
+        r = _renderer(splat, g["aos"], True)
+        r.SetOption(api.OPT_SORT_TILE, tile)
+        fb = _frame(r, g["camera"], g["proj"], 320, 180)
+        _check_tile_lists(r, g["records"], g["order"], 320, 180)
+        out.append((r.Tap(api.TAP_KEYS), r.Tap(api.TAP_VALS), fb))
+    np.testing.assert_array_equal(out[0][0], out[1][0])
+    np.testing.assert_array_equal(out[0][1], out[1][1])
+    np.testing.assert_array_equal(out[0][2], out[1][2])
