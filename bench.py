@@ -337,6 +337,11 @@ def cpu_baseline(workload: str, steps: int, warmup: int, budget_s: float = 150.0
     from splatapult_b200 import scenes
 
     w = WORKLOADS[workload]
+    # all the host threads the box has (torchrun exports OMP_NUM_THREADS=1, which would cripple the CPU arm)
+    try:
+        O.set_num_threads(len(os.sched_getaffinity(0)))
+    except Exception:
+        O.set_num_threads(os.cpu_count() or 1)
     aos, full = O.import_ply(scene_path(workload), True)
     cam = scenes.translate(0, 0, w["cam_z"])
     proj = scenes.perspective(scenes.FOVY, WIDTH / HEIGHT)
@@ -414,6 +419,8 @@ def main():
         import torch.distributed as dist
 
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"  # keep stdout to the one JSON line
         torch.cuda.set_device(local_rank)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     if rank == 0:

@@ -13,12 +13,16 @@
  * The product (splatapult_b200/) never links, imports or calls anything in this directory.
  *
  * PINNING STATUS (see DESIGN.md "Oracle"): the reference has no tests, golden vectors or known-answer
- * fixtures for this path, and its GLSL cannot execute in this container (no OpenGL), so the render
- * stages are "parity unpinned" by the reference itself.  What IS pinned: (a) decode against the
- * reference's only fixture data/test.ply cross-checked with the constants in
- * GaussianCloud::InitDebugCloud (gaussiancloud.cpp:505-578); (b) first-principles known-answer tests
- * derived from the shader math (tests/test_oracle_kat.py); (c) oracle/_ref: the reference's own GLSL
- * shader sources compiled as C++ through a shim (see oracle/glsl_shim) when /root/reference is present.
+ * fixtures for this path and its OpenGL pipeline cannot execute in this container.  The oracle is pinned by
+ * (a) oracle/_ref (oracle/build_ref.py, tests/test_ref_pin.py): the reference's OWN source -- gaussiancloud.cpp,
+ *     ply.cpp, binaryattribute.cpp compiled unmodified against glm/Eigen stand-ins, and the text of
+ *     presort_compute / splat_vert / splat_geom / splat_frag .glsl compiled as C++ against a GLSL shim -- agrees
+ *     with this file BIT FOR BIT on decode, per-gaussian records, draw order and blended framebuffer;
+ * (b) the reference's only data fixture, data/test.ply, cross-checked with the constants hard-coded in
+ *     GaussianCloud::InitDebugCloud (gaussiancloud.cpp:505-578);
+ * (c) first-principles known-answer tests derived from the shader math (tests/test_oracle_kat.py).
+ * What stays outside any pin: the GL driver's own exp/normalize/matrix-product rounding and the fixed-function
+ * rasteriser/ROP, which no source in the reference defines (the shims sum left to right).
  *
  * Third-party arithmetic the reference calls but does not vendor (vcpkg submodule 1b2372fd, glm 1.0.1):
  * glm::inverse(mat4), glm::perspective, mat4*mat4, quat normalize / mat3_cast, mat3*mat3.  Their

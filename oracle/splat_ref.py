@@ -1,0 +1,70 @@
+"""ctypes front-end of oracle/_ref/libsplat_ref.so: the reference's OWN host C++ and GLSL shader source, compiled
+through the shims in oracle/ref_shim and driven by oracle/ref_harness.cpp.  TEST INFRASTRUCTURE ONLY -- used to pin
+the oracle's restatement (tests/test_ref_pin.py); slow, single-threaded, small scenes."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import build_ref
+from .splat_oracle import RECORD_DTYPE
+
+_lib = None
+
+
+def available() -> bool:
+    return build_ref.available() or os.path.exists(build_ref.LIB)
+
+
+def lib() -> C.CDLL:
+    global _lib
+    if _lib is None:
+        path = build_ref.build()
+        if path is None or not os.path.exists(path):
+            raise FileNotFoundError("oracle/_ref/libsplat_ref.so is not built and /root/reference is absent")
+        L = C.CDLL(path)
+        L.ref_import_ply.argtypes = [C.c_char_p, C.c_int, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t), C.POINTER(C.c_int), C.c_void_p, C.c_size_t]
+        L.ref_import_ply.restype = C.c_int
+        L.ref_init_debug_cloud.argtypes = [C.c_void_p, C.c_size_t]
+        L.ref_init_debug_cloud.restype = C.c_int
+        fp = C.POINTER(C.c_float)
+        L.ref_render.argtypes = [C.c_void_p, C.c_size_t, C.c_size_t, C.c_int, C.c_int, fp, fp, fp, fp, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.ref_render.restype = C.c_size_t
+        _lib = L
+    return _lib
+
+
+def import_ply(path: str, import_full_sh: bool = True):
+    """GaussianCloud::ImportPly, executed by the reference's own gaussiancloud.cpp / ply.cpp."""
+    n, stride, full = C.c_size_t(), C.c_size_t(), C.c_int()
+    rc = lib().ref_import_ply(path.encode(), int(import_full_sh), C.byref(n), C.byref(stride), C.byref(full), None, 0)
+    if rc:
+        raise IOError(f"reference ImportPly returned false for {path}")
+    aos = np.zeros((n.value, stride.value // 4), np.float32)
+    rc = lib().ref_import_ply(path.encode(), int(import_full_sh), C.byref(n), C.byref(stride), C.byref(full), aos.ctypes.data, aos.size)
+    assert rc == 0
+    return aos, bool(full.value)
+
+
+def debug_cloud() -> np.ndarray:
+    aos = np.zeros((16, 61), np.float32)
+    n = lib().ref_init_debug_cloud(aos.ctypes.data, aos.size)
+    assert n == 16
+    return aos
+
+
+def render(aos: np.ndarray, full_sh: bool, camera_mat, proj_mat, viewport, near_far, srgb: bool = False):
+    """one frame through the reference's shader source: returns (fb [H,W,4] row 0 = bottom, records, draw order)"""
+    aos = np.ascontiguousarray(aos, np.float32)
+    n, nf = aos.shape
+    f = lambda a, k: np.ascontiguousarray(np.asarray(a, np.float32).reshape(-1)[:k])
+    cam, proj, vp, nfar = f(camera_mat, 16), f(proj_mat, 16), f(viewport, 4), f(near_far, 2)
+    w, h = int(vp[2]), int(vp[3])
+    fb = np.zeros((h, w, 4), np.float32)
+    rec = np.zeros(max(n, 1), RECORD_DTYPE)
+    order = np.zeros(max(n, 1), np.uint32)
+    p = lambda a: a.ctypes.data_as(C.POINTER(C.c_float))
+    v = lib().ref_render(aos.ctypes.data, n, nf * 4, int(full_sh), int(srgb), p(cam), p(proj), p(vp), p(nfar), fb.ctypes.data, rec.ctypes.data, order.ctypes.data)
+    return fb, rec[:n], order[:v].copy()

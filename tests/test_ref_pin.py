@@ -1,0 +1,124 @@
+"""PINS THE ORACLE AGAINST THE REFERENCE'S OWN SOURCE (CPU only).
+
+oracle/_ref/libsplat_ref.so is built by oracle/build_ref.py from /root/reference: the reference's gaussiancloud.cpp /
+ply.cpp / binaryattribute.cpp compiled unmodified against glm/Eigen stand-ins, and the text of its four hot-path
+shaders (presort_compute, splat_vert, splat_geom, splat_frag) compiled as C++ against a GLSL shim and driven with
+the uniforms SplatRenderer::Sort/Render set.  The oracle (oracle/splat_oracle.c) is an independent hand restatement;
+here the two must agree BIT FOR BIT on decode, per-gaussian records, draw order and the blended framebuffer.
+The library travels to the GPU box prebuilt; where neither it nor /root/reference exists the tests skip.
+"""
+import os
+
+import numpy as np
+import pytest
+
+from splatapult_b200 import scenes
+
+NF = [scenes.Z_NEAR, scenes.Z_FAR]
+
+
+@pytest.fixture(scope="module")
+def ref():
+    from oracle import splat_ref
+
+    if not splat_ref.available():
+        pytest.skip("oracle/_ref is not built and /root/reference is absent")
+    splat_ref.lib()
+    return splat_ref
+
+
+def _same_frame(ref, oracle, aos, full, cam, proj, w, h, srgb=False):
+    fb_r, rec_r, order_r = ref.render(aos, full, cam, proj, [0, 0, w, h], NF, srgb=srgb)
+    fb_o, rec_o, order_o, _ = oracle.render(aos, full, cam, proj, [0, 0, w, h], NF, srgb=srgb, want_records=True)
+    np.testing.assert_array_equal(order_r, order_o)
+    for f in rec_o.dtype.names:
+        np.testing.assert_array_equal(rec_r[f], rec_o[f], err_msg=f)
+    np.testing.assert_array_equal(fb_r, fb_o)
+    return fb_o, rec_o, order_o
+
+
+def test_import_ply_is_the_references(ref, oracle, splat, golden_dir, scratch):
+    """GaussianCloud::ImportPly: reference source == oracle == product, bit for bit."""
+    cases = [(os.path.join(golden_dir, "reference_test.ply"), True), (os.path.join(golden_dir, "reference_test.ply"), False)]
+    for deg in (0, 3):
+        p = str(scratch / f"pin_{deg}.ply")
+        scenes.write_synthetic_ply(p, 3000, deg, seed=21 + deg)
+        cases.append((p, True))
+    for path, full in cases:
+        a_ref, f_ref = ref.import_ply(path, full)
+        a_or, f_or = oracle.import_ply(path, full)
+        assert f_ref == f_or
+        np.testing.assert_array_equal(a_ref, a_or)
+        gc = splat.GaussianCloud(import_full_sh=full)
+        assert gc.ImportPly(path) and gc.HasFullSH() == f_ref
+        np.testing.assert_array_equal(gc.GetRawData(), a_ref)
+
+
+def test_debug_cloud_is_the_references(ref, oracle, splat):
+    want = ref.debug_cloud()
+    np.testing.assert_array_equal(oracle.debug_cloud(), want)
+    gc = splat.GaussianCloud()
+    gc.InitDebugCloud()
+    np.testing.assert_array_equal(gc.GetRawData(), want)
+
+
+HEADER_OK = b"ply\nformat binary_little_endian 1.0\nelement vertex 2\nproperty float x\nproperty float y\nproperty float z\nend_header\n"
+
+
+@pytest.mark.parametrize("name,header", [
+    ("ok", HEADER_OK),
+    ("comments", HEADER_OK.replace(b"element", b"comment hi\nelement")),
+    ("aliases", HEADER_OK.replace(b"float x", b"float32 x")),
+    ("crlf", HEADER_OK.replace(b"\n", b"\r\n")),
+    ("big_endian", HEADER_OK.replace(b"little", b"big")),
+    ("second_element", HEADER_OK.replace(b"end_header", b"element face 0\nend_header")),
+    ("list_property", HEADER_OK.replace(b"end_header", b"property list uchar int vertex_indices\nend_header")),
+    ("unknown_type", HEADER_OK.replace(b"float z", b"half z")),
+    ("no_end_header", HEADER_OK.replace(b"end_header\n", b"")),
+])
+def test_ply_reader_decisions_are_the_references(ref, splat, scratch, name, header):
+    path = str(scratch / f"pin_hdr_{name}.ply")
+    with open(path, "wb") as f:
+        f.write(header + np.arange(64, dtype=np.float32).tobytes())
+    try:
+        a_ref, _ = ref.import_ply(path, True)
+        ref_ok = True
+    except IOError:
+        ref_ok = False
+    gc = splat.GaussianCloud()
+    assert gc.ImportPly(path) == ref_ok
+    if ref_ok:
+        np.testing.assert_array_equal(gc.GetRawData(), a_ref)
+
+
+def test_config1_test_ply(ref, oracle, golden_dir):
+    g = np.load(os.path.join(golden_dir, "test_ply_640x480.npz"))
+    aos, full = ref.import_ply(os.path.join(golden_dir, "reference_test.ply"), True)
+    fb, rec, order = _same_frame(ref, oracle, aos, full, g["camera"], g["proj"], 640, 480)
+    np.testing.assert_array_equal(fb, g["fb"])  # and the committed golden is that very frame
+    np.testing.assert_array_equal(order, g["order"])
+
+
+def test_debug_cloud_frame(ref, oracle):
+    _same_frame(ref, oracle, ref.debug_cloud(), False, scenes.translate(0.5, 0.5, 3), scenes.perspective(scenes.FOVY, 320 / 240), 320, 240)
+
+
+@pytest.mark.parametrize("deg,srgb", [(3, False), (0, False), (3, True)])
+def test_synthetic_frames(ref, oracle, scratch, deg, srgb):
+    p = str(scratch / f"pin_scene_{deg}.ply")
+    scenes.write_synthetic_ply(p, 2500, deg, seed=5 + deg)
+    aos, full = ref.import_ply(p, True)
+    assert full == (deg == 3)
+    fb, rec, order = _same_frame(ref, oracle, aos, full, scenes.translate(0.3, -0.2, 9.0), scenes.perspective(scenes.FOVY, 256 / 144), 256, 144, srgb=srgb)
+    assert len(order) > 2000 and np.isfinite(fb).all()
+
+
+def test_culls_and_large_splats(ref, oracle, scratch):
+    """camera inside the cloud: K1 frustum cull, K6 guard band / near plane, splats covering much of the screen."""
+    a = scenes.synthetic_cloud_arrays(3000, 0, seed=8, half_extent=2.0)
+    a["log_scale"][:60] += 2.0
+    p = scenes.write_ply_from_arrays(str(scratch / "pin_inside.ply"), a)
+    aos, full = ref.import_ply(p, True)
+    cam = scenes.look_at_camera((0.3, 0.2, 0.1), (1.0, 0.4, -2.0))
+    fb, rec, order = _same_frame(ref, oracle, aos, full, cam, scenes.perspective(scenes.FOVY, 160 / 120), 160, 120)
+    assert 0.05 < rec["visible"].mean() < 0.8
