@@ -189,7 +189,7 @@ def run_ours(args, rank, local_rank, world):
         del buf
     load_s = time.perf_counter() - t0
 
-    r.SetOption(api.OPT_SORT_MODE, api.SORT_LSD if args.sort_mode == "lsd" else api.SORT_BINNED)
+    r.SetOption(api.OPT_SORT_MODE, {"lsd": api.SORT_LSD, "lsd_flat": api.SORT_LSD_FLAT, "binned": api.SORT_BINNED}[args.sort_mode])
     r.SetOption(api.OPT_SORT_TILE, args.sort_tile)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
 
@@ -283,12 +283,24 @@ def run_ours(args, rank, local_rank, world):
                 "segment_sort": (stages[2], ab["segment_sort"], stages[2]), "bin_scatter": (stages[1], ab["bin_scatter"], stages[1])}
         stage_gbs = {k: (ab[k] / (stage[k] * 1e-3) / 1e9 if stage[k] > 0 else None) for k in ("project", "bin_scatter", "segment_sort", "composite")}
     else:
-        stage = {"project": stages[0], "sort_histogram": stages[1], "sort_passes_total": stages[2], "tile_ranges": stages[3],
-                 "composite": stages[4], "frame": stages[7]}
-        pass_ms = stages[2] / max(int(st.sort_passes), 1)
+        split = int(st.sort_mode) == api.SORT_LSD  # depth digits sorted on the N gaussians, tile digits on the D instances
+        d_passes = int(st.sort_passes) - 4 if split else int(st.sort_passes)  # onesweep passes that run on the D instances
+        if split:
+            # project_keys writes 12 B key/id + 8 B rectangle per gaussian instead of 12 B per instance;
+            # stage 1 = 4 depth-digit passes on N pairs (24 N each) + expansion (20 N in, 12 D out)
+            ab["project"] = ab["project"] - 12 * d + 20 * n
+            ab["depth_sort_emit"] = 4 * 24 * n + 20 * n + 12 * d
+            ab["frame"] = ab["project"] + ab["depth_sort_emit"] + d_passes * ab["sort_pass"] + ab["tile_ranges"] + ab["composite"]
+            stage = {"project": stages[0], "depth_sort_emit": stages[1], "tile_sort_passes_total": stages[2], "tile_ranges": stages[3],
+                     "composite": stages[4], "frame": stages[7]}
+            names = ("project", "depth_sort_emit", "tile_ranges", "composite")
+        else:
+            stage = {"project": stages[0], "sort_passes_total": stages[2], "tile_ranges": stages[3], "composite": stages[4], "frame": stages[7]}
+            names = ("project", "tile_ranges", "composite")
+        pass_ms = stages[2] / max(d_passes, 1)
         cand = {"composite": (stages[4], ab["composite"], stages[4]), "sort_onesweep": (stages[2], ab["sort_pass"], pass_ms),
                 "project": (stages[0], ab["project"], stages[0])}
-        stage_gbs = {k: (ab[k] / (stage[k] * 1e-3) / 1e9 if stage[k] > 0 else None) for k in ("project", "sort_histogram", "tile_ranges", "composite")}
+        stage_gbs = {k: (ab[k] / (stage[k] * 1e-3) / 1e9 if stage[k] > 0 else None) for k in names}
         stage_gbs["sort_pass"] = ab["sort_pass"] / (pass_ms * 1e-3) / 1e9 if pass_ms > 0 else None
     dom = max(cand, key=lambda k: cand[k][0])
     dom_total, dom_bytes, dom_launch_ms = cand[dom]
@@ -309,7 +321,7 @@ def run_ours(args, rank, local_rank, world):
         "config": {"workload": f"{args.workload}: {w['cfg']} of BASELINE.json -- {n} synthetic gaussians (seed {w['seed']}), SH degree {w['deg']}, "
                                f"{WIDTH}x{HEIGHT}, {'fp16' if w['fp16'] else 'fp32'} framebuffer, one view per GPU",
                    "l2": "flushed between timed frames (256 MiB memset, untimed); e2e loop: per-frame working set > L2",
-                   "tile": 16, "early_out_T": 1e-4, "sort": "binned: MSD by tile id + per-tile smem sort" if binned else "lsd: device-wide onesweep", "sort_bits": int(st.sort_bits), "sort_passes": int(st.sort_passes),
+                   "tile": 16, "early_out_T": 1e-4, "sort": args.sort_mode + {"lsd": ": onesweep LSD, depth digits on N gaussians + tile digits on D instances", "lsd_flat": ": onesweep LSD, all digits on D instances", "binned": ": MSD by tile id + per-tile smem sort"}[args.sort_mode],"sort_bits": int(st.sort_bits), "sort_passes": int(st.sort_passes),
                    "visible": v, "tile_instances": d, "parallelism": f"views x{world}"},
         "frames_per_s": args.steps * world / secs,
         "sort_gkeys_per_s": (d / ((stages[1] + stages[2]) * 1e-3) / 1e9) if (stages[1] + stages[2]) > 0 else None,
@@ -398,7 +410,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="1m_deg0", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--sort-mode", default="lsd", choices=["binned", "lsd"])
+    ap.add_argument("--sort-mode", default="lsd", choices=["binned", "lsd", "lsd_flat"])
     ap.add_argument("--sort-tile", type=int, default=4096, choices=[2048, 4096])
     args = ap.parse_args()
 

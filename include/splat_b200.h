@@ -139,7 +139,9 @@ enum {
 };
 enum {
     SPL_SORT_BINNED = 0, /* MSD: counting sort on the tile id, then per-tile shared-memory sort of (depthKey, id) */
-    SPL_SORT_LSD = 1     /* device-wide onesweep LSD radix sort of the packed (tile << 32 | depthKey) u64 keys */
+    SPL_SORT_LSD = 1,    /* device-wide onesweep LSD radix sort of the packed (tile << 32 | depthKey) u64 keys; the four
+                            depth-digit passes run on the N gaussians before tile expansion, the tile-digit passes on the D instances */
+    SPL_SORT_LSD_FLAT = 2 /* same sort with every digit pass on the D instances (the textbook arrangement; slower) */
 };
 SPL_API int spl_renderer_set_option(spl_renderer*, int option, double value);
 

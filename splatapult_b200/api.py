@@ -19,6 +19,7 @@ OPT_SORT_MODE = 3
 OPT_SORT_TILE = 4
 SORT_BINNED = 0
 SORT_LSD = 1
+SORT_LSD_FLAT = 2
 
 TAP_RECORDS = 0
 TAP_KEYS = 1

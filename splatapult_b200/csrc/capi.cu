@@ -263,7 +263,7 @@ int spl_sorter_sort(spl_sorter* s, void* d_keys_in, void* d_vals_in, void* d_key
         SORTER_TRY(cudaMemsetAsync(s->status, 0, splat::sort_status_bytes(s->capacity, splat::kMaxSortPasses), stream));
         ++s->generation;
     }
-    splat::SortWorkspace ws{ctl + 64, s->status, ctl + 8, s->capacity, s->generation, s->keysPerThread};
+    splat::SortWorkspace ws{ctl + 64, s->status, ctl + 8, s->capacity, s->generation, s->keysPerThread, 0};
     auto* kin = static_cast<unsigned long long*>(d_keys_in);
     auto* kout = static_cast<unsigned long long*>(d_keys_out);
     auto* vin = static_cast<uint32_t*>(d_vals_in);

@@ -84,7 +84,7 @@ struct FrameCounters
     unsigned int projectTicket;         // dynamic block ids of the projection kernel
     unsigned int sortTickets[kMaxSortPasses];
     unsigned int largeTiles;            // tiles whose segment exceeds kSegSortSmallCap (binned sort)
-    unsigned int pad[1];
+    unsigned int sortCount;             // elements of the per-gaussian depth sort (default LSD path): N
 };
 
 // ---------------------------------------------------------------------------------------------------
@@ -147,6 +147,13 @@ __device__ __forceinline__ unsigned long long ld_relaxed_u64(const unsigned long
 __device__ __forceinline__ void st_relaxed_u64(unsigned long long* p, unsigned long long v)
 {
     asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+// shared-memory reduction without nvcc's automatic warp-aggregation loop (which costs ~one iteration per distinct
+// address in the warp -- a pessimisation for histogram updates whose addresses are mostly distinct)
+__device__ __forceinline__ void smem_red_add(uint32_t* p, uint32_t v)
+{
+    asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(smem_u32(p)), "r"(v) : "memory");
 }
 
 __device__ __forceinline__ float ex2_approx(float x)

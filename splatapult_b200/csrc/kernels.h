@@ -21,6 +21,15 @@ uint32_t project_num_blocks(uint32_t n);
 cudaError_t launch_project(const PackedCloud& cloud, const FrameConstants& fc, ProjRecord* rec, unsigned long long* keys, uint32_t* vals,
                            FrameCounters* ctr, unsigned long long* scanState, uint32_t capacity, uint32_t* digit0Hist, cudaStream_t stream);
 
+// default LSD path: (1) project + one (depthKey, id) pair and an 8-byte tile rectangle per gaussian; after the depth
+// digits have been sorted on those N pairs, (2) expand the sorted list into (tile << 32 | depthKey, id) instances in
+// depth order (scan + coalesced emission) and leave the histogram of the first tile digit in tileDigitHist
+cudaError_t launch_project_keys(const PackedCloud& cloud, const FrameConstants& fc, ProjRecord* rec, unsigned long long* keys, uint32_t* vals,
+                                uint2* side, FrameCounters* ctr, uint32_t* digit0Hist, cudaStream_t stream);
+cudaError_t launch_emit_sorted(const unsigned long long* sortedKeys, const uint32_t* sortedVals, const uint2* side, uint32_t n,
+                               const FrameConstants& fc, unsigned long long* keys, uint32_t* vals, FrameCounters* ctr,
+                               unsigned long long* scanState, uint32_t capacity, uint32_t* tileDigitHist, cudaStream_t stream);
+
 cudaError_t launch_project_bin(const PackedCloud& cloud, const FrameConstants& fc, ProjRecord* rec, uint4* side, uint32_t* tileCount,
                                FrameCounters* ctr, cudaStream_t stream);
 cudaError_t launch_bin_instances(const uint4* side, uint32_t n, int tilesX, uint32_t* tileCursor, unsigned long long* pairs, uint32_t capacity,
@@ -36,12 +45,15 @@ cudaError_t launch_segment_sort(unsigned long long* pairs, unsigned long long* s
 // ---- radix_sort.cu : device-wide LSD radix sort of (u64 key, u32 value) pairs, 8-bit digits, onesweep style
 struct SortWorkspace
 {
-    uint32_t* histograms;         // [kMaxSortPasses][256] global digit counts; row 0 filled by the producer, row p+1 by pass p
-    unsigned long long* status;   // [passes][tiles][256] decoupled look-back words {flag, generation, count}
-    uint32_t* tickets;            // [kMaxSortPasses] dynamic tile ids (zeroed per sort)
+    uint32_t* histograms;         // [kMaxSortPasses][256] global digit counts; a sort's first row is filled by its producer,
+                                  // row p+1 by pass p
+    unsigned long long* status;   // look-back words, sort_status_bytes(capacity, kMaxSortPasses) bytes (never cleared per sort)
+    uint32_t* tickets;            // [kMaxSortPasses] dynamic tile ids (zeroed per frame)
     uint64_t capacity;            // keys the status array was sized for
-    uint32_t generation;          // distinguishes this sort's look-back words from stale ones (16 bits used)
+    uint32_t generation;          // distinguishes this frame's look-back words from stale ones (16 bits used)
     int keysPerThread;            // 16 (4096-key tiles, 3 CTAs/SM) or 8 (2048-key tiles, 5 CTAs/SM)
+    int passOffset;               // first histogram row / ticket / status region this sort uses (0..kMaxSortPasses-1):
+                                  // lets two sorts of one frame (depth digits on N, tile digits on D) share the workspace
 };
 size_t sort_status_bytes(uint64_t capacity, int passes);
 // keys/vals ping-pong between (A) and (B); passes = ceil((endBit-beginBit)/8); the sorted result is in A when

@@ -247,27 +247,56 @@ __device__ __forceinline__ Projected project_gaussian(const PackedCloud& cloud, 
     return out;
 }
 
-template <int SH_MODE>
+// Two uses of one kernel body (scan of tile counts + coalesced key emission):
+//   FROM_SORTED = false ("flat" LSD path): projects gaussian i itself and emits its keys in index order; the
+//       histogram it leaves for the sorter is that of the keys' LOWEST digit (weighted by the tile count);
+//   FROM_SORTED = true (default LSD path): entry j of the depth-sorted gaussian list (sortedKeys low word = depthKey,
+//       sortedVals = gaussian id, side[id] = tile rectangle) -- the projection was done by k_project_keys and the
+//       four depth-digit passes have already run on the N gaussians; keys are emitted in depth order and the
+//       histogram is that of the FIRST TILE digit (bits 32..39), one count per instance.
+template <int SH_MODE, bool FROM_SORTED>
 __global__ void __launch_bounds__(kProjThreads)
 k_project(const PackedCloud cloud, const __grid_constant__ FrameConstants fc, ProjRecord* __restrict__ rec,
           unsigned long long* __restrict__ keys, uint32_t* __restrict__ vals, FrameCounters* __restrict__ ctr,
-          unsigned long long* __restrict__ scanState, uint32_t capacity, uint32_t* __restrict__ digit0Hist)
+          unsigned long long* __restrict__ scanState, uint32_t capacity, uint32_t* __restrict__ digit0Hist,
+          const unsigned long long* __restrict__ sortedKeys, const uint32_t* __restrict__ sortedVals, const uint2* __restrict__ side,
+          uint32_t nSorted)
 {
     __shared__ uint32_t sBlockId;
     __shared__ uint32_t sWarpTotal[kProjThreads / 32];
     __shared__ unsigned long long sBlockBase;
-    __shared__ uint32_t sDigit0[kRadixSize];  // histogram of the emitted keys' lowest digit (saves the sorter a pass)
+    __shared__ uint32_t sDigit0[kRadixSize];  // histogram of the emitted keys' next sort digit (saves the sorter a pass)
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid == 0) sBlockId = atomicAdd(&ctr->projectTicket, 1u);  // dynamic id: predecessors are resident or done
     sDigit0[tid] = 0;
     __syncthreads();
     const uint32_t vbid = sBlockId;
-    const uint32_t i = vbid * kProjThreads + tid;
-    const Projected pg = project_gaussian<SH_MODE>(cloud, fc, rec, i, i < cloud.n);
-    const uint32_t count = pg.count, refKey = pg.refKey;
-    const uint32_t rect = pg.x0 | (pg.y0 << 10) | ((pg.w ? pg.w - 1 : 0) << 20);
-    const bool visible = pg.visible;
+    uint32_t i = vbid * kProjThreads + tid;  // gaussian id
+    uint32_t count = 0, refKey = 0, rect = 0;
+    bool visible = false;
+    if (FROM_SORTED)
+    {
+        const uint32_t j = i;
+        i = 0;
+        if (j < nSorted)
+        {
+            i = __ldg(sortedVals + j);
+            const uint2 sd = __ldg(side + i);
+            const uint32_t w = sd.y & 0xffffu, h = sd.y >> 16;
+            count = w * h;
+            rect = (sd.x & 0xffffu) | ((sd.x >> 16) << 10) | ((w ? w - 1 : 0) << 20);
+            refKey = (uint32_t)__ldg(sortedKeys + j);
+        }
+    }
+    else
+    {
+        const Projected pg = project_gaussian<SH_MODE>(cloud, fc, rec, i, i < cloud.n);
+        count = pg.count;
+        refKey = pg.refKey;
+        rect = pg.x0 | (pg.y0 << 10) | ((pg.w ? pg.w - 1 : 0) << 20);
+        visible = pg.visible;
+    }
 
     // ---- block-wide exclusive scan of the tile counts
     uint32_t incl = count;
@@ -332,8 +361,8 @@ k_project(const PackedCloud cloud, const __grid_constant__ FrameConstants fc, Pr
     const uint32_t cntE = fits ? count : 0u;
     if (!fits) atomicOr(&ctr->overflow, 1u);
     const uint32_t gOff = fits ? (uint32_t)gOff64 : 0u;
-    // all cntE keys of this gaussian share their low 32 bits: one weighted update covers them
-    if (cntE && digit0Hist) atomicAdd(&sDigit0[refKey & (kRadixSize - 1)], cntE);
+    // flat path: all cntE keys of this gaussian share their low 32 bits, one weighted update covers them
+    if (!FROM_SORTED && cntE && digit0Hist) smem_red_add(&sDigit0[refKey & (kRadixSize - 1)], cntE);
 
     uint32_t inclE = cntE;
 #pragma unroll
@@ -375,6 +404,7 @@ k_project(const PackedCloud cloud, const __grid_constant__ FrameConstants fc, Pr
             const uint32_t tile = (y0 + row) * tilesX + (x0 + col);
             keys[oOff + k] = ((unsigned long long)tile << 32) | oKey;
             vals[oOff + k] = oId;
+            if (FROM_SORTED && digit0Hist) smem_red_add(&sDigit0[tile & (kRadixSize - 1)], 1u);  // first tile digit
         }
     }
     if (digit0Hist)
@@ -383,6 +413,40 @@ k_project(const PackedCloud cloud, const __grid_constant__ FrameConstants fc, Pr
         const uint32_t c = sDigit0[tid];
         if (c) atomicAdd(digit0Hist + tid, c);
     }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// default LSD path, step 1: project every gaussian and leave ONE (depthKey, id) pair per gaussian for the sorter
+// plus an 8-byte side record with its tile rectangle.  Gaussians that touch no tile get depthKey 0xFFFFFFFF (they
+// sort to the end and expand to nothing).  No scan, no atomics besides the per-CTA histogram flush.
+// ---------------------------------------------------------------------------------------------------
+template <int SH_MODE>
+__global__ void __launch_bounds__(kProjThreads)
+k_project_keys(const PackedCloud cloud, const __grid_constant__ FrameConstants fc, ProjRecord* __restrict__ rec,
+               unsigned long long* __restrict__ keys, uint32_t* __restrict__ vals, uint2* __restrict__ side, FrameCounters* __restrict__ ctr,
+               uint32_t* __restrict__ digit0Hist)
+{
+    __shared__ uint32_t sDigit0[kRadixSize];
+    const int tid = threadIdx.x, lane = tid & 31;
+    sDigit0[tid] = 0;
+    __syncthreads();
+    const uint32_t i = blockIdx.x * kProjThreads + tid;
+    const bool inRange = i < cloud.n;
+    const Projected pg = project_gaussian<SH_MODE>(cloud, fc, rec, i, inRange);
+    if (inRange)
+    {
+        const uint32_t key = pg.count ? pg.refKey : 0xFFFFFFFFu;
+        keys[i] = key;
+        vals[i] = i;
+        side[i] = pg.count ? make_uint2(pg.x0 | (pg.y0 << 16), pg.w | (pg.h << 16)) : make_uint2(0u, 0u);
+        smem_red_add(&sDigit0[key & (kRadixSize - 1)], 1u);
+    }
+    const uint32_t nVisibleWarp = __popc(__ballot_sync(0xffffffffu, pg.visible));
+    if (lane == 0 && nVisibleWarp) atomicAdd(&ctr->visible, nVisibleWarp);
+    if (blockIdx.x == 0 && tid == 0) ctr->sortCount = cloud.n;
+    __syncthreads();
+    const uint32_t c = sDigit0[tid];
+    if (c) atomicAdd(digit0Hist + tid, c);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -519,10 +583,36 @@ cudaError_t launch_project(const PackedCloud& cloud, const FrameConstants& fc, P
     if (blocks == 0) return cudaSuccess;
     switch (cloud.shMode)
     {
-    case 0: k_project<0><<<blocks, kProjThreads, 0, stream>>>(cloud, fc, rec, keys, vals, ctr, scanState, capacity, digit0Hist); break;
-    case 1: k_project<1><<<blocks, kProjThreads, 0, stream>>>(cloud, fc, rec, keys, vals, ctr, scanState, capacity, digit0Hist); break;
-    default: k_project<3><<<blocks, kProjThreads, 0, stream>>>(cloud, fc, rec, keys, vals, ctr, scanState, capacity, digit0Hist); break;
+    case 0: k_project<0, false><<<blocks, kProjThreads, 0, stream>>>(cloud, fc, rec, keys, vals, ctr, scanState, capacity, digit0Hist, nullptr, nullptr, nullptr, 0); break;
+    case 1: k_project<1, false><<<blocks, kProjThreads, 0, stream>>>(cloud, fc, rec, keys, vals, ctr, scanState, capacity, digit0Hist, nullptr, nullptr, nullptr, 0); break;
+    default: k_project<3, false><<<blocks, kProjThreads, 0, stream>>>(cloud, fc, rec, keys, vals, ctr, scanState, capacity, digit0Hist, nullptr, nullptr, nullptr, 0); break;
     }
+    return cudaGetLastError();
+}
+
+cudaError_t launch_project_keys(const PackedCloud& cloud, const FrameConstants& fc, ProjRecord* rec, unsigned long long* keys, uint32_t* vals,
+                                uint2* side, FrameCounters* ctr, uint32_t* digit0Hist, cudaStream_t stream)
+{
+    const uint32_t blocks = project_num_blocks(cloud.n);
+    if (blocks == 0) return cudaSuccess;
+    switch (cloud.shMode)
+    {
+    case 0: k_project_keys<0><<<blocks, kProjThreads, 0, stream>>>(cloud, fc, rec, keys, vals, side, ctr, digit0Hist); break;
+    case 1: k_project_keys<1><<<blocks, kProjThreads, 0, stream>>>(cloud, fc, rec, keys, vals, side, ctr, digit0Hist); break;
+    default: k_project_keys<3><<<blocks, kProjThreads, 0, stream>>>(cloud, fc, rec, keys, vals, side, ctr, digit0Hist); break;
+    }
+    return cudaGetLastError();
+}
+
+cudaError_t launch_emit_sorted(const unsigned long long* sortedKeys, const uint32_t* sortedVals, const uint2* side, uint32_t n,
+                               const FrameConstants& fc, unsigned long long* keys, uint32_t* vals, FrameCounters* ctr,
+                               unsigned long long* scanState, uint32_t capacity, uint32_t* tileDigitHist, cudaStream_t stream)
+{
+    const uint32_t blocks = project_num_blocks(n);
+    if (blocks == 0) return cudaSuccess;
+    PackedCloud none{};
+    k_project<0, true><<<blocks, kProjThreads, 0, stream>>>(none, fc, nullptr, keys, vals, ctr, scanState, capacity, tileDigitHist, sortedKeys, sortedVals,
+                                                           side, n);
     return cudaGetLastError();
 }
 

@@ -89,7 +89,7 @@ k_sort_histogram(const unsigned long long* __restrict__ keys, const uint32_t* __
         for (int k = 0; k < kSortTileKeys / kHistThreads; k++)
         {
             const uint32_t idx = k * kHistThreads + tid;
-            if (idx < cnt) atomicAdd(&sHist[digit_of(sKeys[buf][idx], shift, mask)], 1u);
+            if (idx < cnt) smem_red_add(&sHist[digit_of(sKeys[buf][idx], shift, mask)], 1u);
         }
         __syncthreads();  // all reads of sKeys[buf] done before it is refilled two tiles from now
         buf ^= 1;
@@ -214,7 +214,7 @@ k_sort_onesweep(const unsigned long long* __restrict__ keysIn, const uint32_t* _
             for (int j = 0; j < KPT; j++)
             {
                 const uint32_t idx = warp * (KPT * 32) + j * 32 + lane;
-                if (idx < nValid) atomicAdd(&s.nextHist[digit_of(key[j], nextShift, nextMask)], 1u);
+                if (idx < nValid) smem_red_add(&s.nextHist[digit_of(key[j], nextShift, nextMask)], 1u);
             }
         }
         __syncthreads();
@@ -362,8 +362,8 @@ static cudaError_t launch_passes_t(unsigned long long* keysA, uint32_t* valsA, u
         const int nshift = last ? 0 : shift + kRadixBits;
         k_sort_onesweep<KPT><<<grid, kSortThreads, sizeof(Smem), stream>>>(
             kin, vin, kout, vout, nDevice, shift, digit_mask(shift, endBit), nshift, last ? 0u : digit_mask(nshift, endBit),
-            ws.histograms + p * kRadixSize, last ? nullptr : ws.histograms + (p + 1) * kRadixSize,
-            ws.status + (size_t)p * maxTiles * kRadixSize, ws.tickets + p, ws.generation);
+            ws.histograms + (ws.passOffset + p) * kRadixSize, last ? nullptr : ws.histograms + (ws.passOffset + p + 1) * kRadixSize,
+            ws.status + (size_t)(ws.passOffset + p) * maxTiles * kRadixSize, ws.tickets + ws.passOffset + p, ws.generation);
     }
     return cudaGetLastError();
 }
@@ -383,7 +383,8 @@ cudaError_t launch_sort_histogram(const unsigned long long* keysA, const uint32_
     }
     const uint32_t capTiles = (uint32_t)((capacity + kSortTileKeys - 1) / kSortTileKeys);
     const uint32_t grid = max(1u, min((uint32_t)numSMs * 3u, capTiles));
-    k_sort_histogram<<<grid, kHistThreads, smem, stream>>>(keysA, nDevice, beginBit, digit_mask(beginBit, endBit), ws.histograms);
+    k_sort_histogram<<<grid, kHistThreads, smem, stream>>>(keysA, nDevice, beginBit, digit_mask(beginBit, endBit),
+                                                           ws.histograms + ws.passOffset * kRadixSize);
     return cudaGetLastError();
 }
 

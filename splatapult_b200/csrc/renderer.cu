@@ -59,6 +59,8 @@ struct RendererImpl
     unsigned long long* dScan = nullptr;
     unsigned long long* dStatus = nullptr;
     uint32_t sortGeneration = 0;
+    const unsigned long long* dSortedKeys = nullptr;  // where the last LSD sort left its result
+    const uint32_t* dSortedVals = nullptr;
     int sortKpt = 16;
     uint2* dRanges = nullptr;
     uint32_t* dTileCtl = nullptr;  // tileCount | tileCursor | largeList, rangesTiles words each
@@ -295,23 +297,54 @@ struct RendererImpl
         }
         else
         {
-            // LSD: device-wide onesweep radix sort of the packed u64 keys, then boundary detection
+            // LSD: device-wide onesweep radix sort of the packed (tile << 32 | depthKey) keys, then boundary detection.
             // look-back words are generation-tagged instead of cleared; re-zero only when the 16-bit tag wraps
             if (((++sortGeneration) & 0xffffu) == 0)
             {
                 CU_TRY(cudaMemsetAsync(dStatus, 0, sort_status_bytes(capacity, kMaxSortPasses), stream));
                 ++sortGeneration;
             }
-            // the projection kernel also produces the first digit's histogram; pass p produces pass p+1's
-            CU_TRY(launch_project(cloud, fc, dRec, dKeysA, dValsA, dCtr, dScan, (uint32_t)capacity, dHist, stream));
-            launches += n ? 1 : 0;
-            if (profile) CU_TRY(cudaEventRecord(ev[1], stream));
-            if (profile) CU_TRY(cudaEventRecord(ev[6], stream));
-            SortWorkspace ws{dHist, dStatus, dCtr->sortTickets, capacity, sortGeneration, sortKpt};
-            CU_TRY(launch_sort_passes(dKeysA, dValsA, dKeysB, dValsB, &dCtr->usedInstances, capacity, 0, sortBits, ws, numSMs, stream));
-            launches += sortPasses;
+            if (frameSortMode == SPL_SORT_LSD_FLAT)
+            {
+                // every digit pass runs on the D tile instances (emitted in gaussian order by the projection kernel,
+                // which also produces the first digit's histogram; pass p produces pass p+1's)
+                CU_TRY(launch_project(cloud, fc, dRec, dKeysA, dValsA, dCtr, dScan, (uint32_t)capacity, dHist, stream));
+                launches += n ? 1 : 0;
+                if (profile) CU_TRY(cudaEventRecord(ev[1], stream));
+                if (profile) CU_TRY(cudaEventRecord(ev[6], stream));
+                SortWorkspace ws{dHist, dStatus, dCtr->sortTickets, capacity, sortGeneration, sortKpt, 0};
+                CU_TRY(launch_sort_passes(dKeysA, dValsA, dKeysB, dValsB, &dCtr->usedInstances, capacity, 0, sortBits, ws, numSMs, stream));
+                launches += sortPasses;
+                dSortedKeys = (sortPasses & 1) ? dKeysB : dKeysA;
+                dSortedVals = (sortPasses & 1) ? dValsB : dValsA;
+            }
+            else
+            {
+                // the four depth digits are common to all instances of a gaussian: those passes run on the N
+                // (depthKey, id) pairs BEFORE tile expansion; the expansion emits in depth order; only the tile digits
+                // are sorted on the D instances.  Same stable LSD sort of the same keys, half the element-passes.
+                const int tileBits = sortBits - kDepthBits, tilePasses = (tileBits + kRadixBits - 1) / kRadixBits;
+                CU_TRY(launch_project_keys(cloud, fc, dRec, dKeysA, dValsA, reinterpret_cast<uint2*>(dSide), dCtr, dHist, stream));
+                launches += n ? 1 : 0;
+                if (profile) CU_TRY(cudaEventRecord(ev[1], stream));
+                SortWorkspace wsDepth{dHist, dStatus, dCtr->sortTickets, capacity, sortGeneration, sortKpt, 0};
+                CU_TRY(launch_sort_passes(dKeysA, dValsA, dKeysB, dValsB, &dCtr->sortCount, capacity, 0, kDepthBits, wsDepth, numSMs, stream));
+                CU_TRY(launch_emit_sorted(dKeysA, dValsA, reinterpret_cast<const uint2*>(dSide), n, fc, dKeysB, dValsB, dCtr, dScan, (uint32_t)capacity,
+                                          dHist + 4 * kRadixSize, stream));
+                launches += 4 + (n ? 1 : 0);
+                if (profile) CU_TRY(cudaEventRecord(ev[6], stream));
+                dSortedKeys = dKeysB;
+                dSortedVals = dValsB;
+                if (tilePasses > 0)
+                {
+                    SortWorkspace wsTile{dHist, dStatus, dCtr->sortTickets, capacity, sortGeneration, sortKpt, 4};
+                    CU_TRY(launch_sort_passes(dKeysB, dValsB, dKeysA, dValsA, &dCtr->usedInstances, capacity, kDepthBits, sortBits, wsTile, numSMs, stream));
+                    launches += tilePasses;
+                    if (tilePasses & 1) { dSortedKeys = dKeysA; dSortedVals = dValsA; }
+                }
+            }
             if (profile) CU_TRY(cudaEventRecord(ev[2], stream));
-            CU_TRY(launch_tile_ranges(sortedKeys(), &dCtr->usedInstances, capacity, dRanges, numTiles, numSMs, stream));
+            CU_TRY(launch_tile_ranges(dSortedKeys, &dCtr->usedInstances, capacity, dRanges, numTiles, numSMs, stream));
             launches += 1;
             if (profile) CU_TRY(cudaEventRecord(ev[3], stream));
         }
@@ -319,8 +352,8 @@ struct RendererImpl
         return ok();
     }
 
-    const unsigned long long* sortedKeys() const { return (sortPasses & 1) ? dKeysB : dKeysA; }
-    const uint32_t* sortedVals() const { return (sortPasses & 1) ? dValsB : dValsA; }
+    const unsigned long long* sortedKeys() const { return dSortedKeys; }
+    const uint32_t* sortedVals() const { return dSortedVals; }
 
     int render(const float* cam, const float* proj, const float* vp, const float* nf)
     {
@@ -435,7 +468,7 @@ struct RendererImpl
         out->instance_capacity = capacity;
         out->overflow = c.overflow;
         out->tiles_x = fc.tilesX; out->tiles_y = fc.tilesY; out->tile_size = kTileSize;
-        out->sort_passes = frameSortMode == SPL_SORT_BINNED ? 1 : sortPasses; out->sort_bits = sortBits;
+        out->sort_passes = frameSortMode == SPL_SORT_BINNED ? 1 : sortPasses;  // LSD: 4 depth-digit passes + tile-digit passes out->sort_bits = sortBits;
         out->sort_mode = frameSortMode;
         out->sh_mode = cloud.shMode;
         out->kernel_launches = launches;
@@ -595,7 +628,7 @@ bool SplatRenderer::SetOption(int option, double value)
         impl->sortKpt = value == 2048 ? 8 : 16;
         break;
     case SPL_OPT_SORT_MODE:
-        if (value != SPL_SORT_BINNED && value != SPL_SORT_LSD) { status = SPL_ERR_ARG; error = "unknown sort mode"; return false; }
+        if (value != SPL_SORT_BINNED && value != SPL_SORT_LSD && value != SPL_SORT_LSD_FLAT) { status = SPL_ERR_ARG; error = "unknown sort mode"; return false; }
         impl->sortMode = (int)value;
         impl->haveSort = false;
         break;

@@ -22,7 +22,7 @@ NF = [scenes.Z_NEAR, scenes.Z_FAR]
 SORT_MODE = api.SORT_BINNED
 
 
-@pytest.fixture(params=[api.SORT_BINNED, api.SORT_LSD], ids=["binned", "lsd"], autouse=True)
+@pytest.fixture(params=[api.SORT_LSD, api.SORT_LSD_FLAT, api.SORT_BINNED], ids=["lsd", "lsd_flat", "binned"], autouse=True)
 def sort_mode(request):
     """every test runs on both frame-sort paths: MSD-by-tile (default) and the device-wide LSD onesweep"""
     global SORT_MODE
@@ -333,8 +333,8 @@ def test_dense_tile_segments(splat, oracle, scratch, n, expect_path):
 
 def test_sort_tile_variants_give_identical_lists(splat, golden_dir):
     """the onesweep sorter's two tile sizes (4096 / 2048 keys per CTA) are the same stable sort"""
-    if SORT_MODE != api.SORT_LSD:
-        pytest.skip("LSD path only")
+    if SORT_MODE == api.SORT_BINNED:
+        pytest.skip("LSD paths only")
     g = np.load(os.path.join(golden_dir, "synth_2k_deg3_320x180.npz"))
     out = []
     for tile in (4096, 2048):
