@@ -72,7 +72,7 @@ struct CompSmem
 };
 
 template <bool HALF>
-__global__ void __launch_bounds__(kCompThreads)
+__global__ void __launch_bounds__(kCompThreads, 6)
 k_composite(const uint2* __restrict__ ranges, const uint32_t* __restrict__ vals, int idStride, const ProjRecord* __restrict__ rec,
             void* __restrict__ fb, int width, int height, int tilesX, float earlyOutT)
 {

@@ -59,7 +59,7 @@ __device__ __forceinline__ float srgb_to_linear(float s)
 
 // splat_vert.glsl:51-127; sh planes hold vec4 blocks {r,g,b}_sh{0..3}
 template <int SH_MODE>
-__device__ __forceinline__ void radiance(const PackedCloud& cloud, uint32_t i, float vx, float vy, float vz, float* rgb)
+__device__ __forceinline__ void radiance(const PackedCloud& cloud, uint32_t i, float vx, float vy, float vz, float* rgb, const float* dcPre)
 {
     float b[16];
     const float vx2 = vx * vx, vy2 = vy * vy, vz2 = vz * vz;
@@ -93,7 +93,7 @@ __device__ __forceinline__ void radiance(const PackedCloud& cloud, uint32_t i, f
         if (SH_MODE == 0)
         {
             // degree-1 slots are exact zeros in this layout: b[k]*0 contributes +-0 and cannot change acc
-            acc = b[0] * __ldg(cloud.dc[c] + i);
+            acc = b[0] * dcPre[c];  // prefetched with the position
         }
         else if (SH_MODE == 1)
         {
@@ -145,6 +145,17 @@ __device__ __forceinline__ Projected project_gaussian(const PackedCloud& cloud, 
     {
         const float4 pa = __ldg(cloud.posAlpha + i);
         const float x = pa.x, y = pa.y, z = pa.z, alpha = pa.w;
+        // speculative: Sigma (and the DC colour) are fetched together with the position instead of after the cull
+        // decision -- one memory round trip per gaussian instead of two (almost every gaussian survives the cull in
+        // the benchmark scenes; a culled one costs 36-48 wasted bytes)
+        const float4 ca = __ldg(cloud.covA + i), cb = __ldg(cloud.covB + i);
+        const float cc = __ldg(cloud.covC + i);
+        float dcPre[3] = {0.0f, 0.0f, 0.0f};
+        if (SH_MODE == 0)
+        {
+#pragma unroll
+            for (int c = 0; c < 3; c++) dcPre[c] = __ldg(cloud.dc[c] + i);
+        }
 
         // ---- K1 presort_compute.glsl:42-56
         float p[4];
@@ -183,8 +194,7 @@ __device__ __forceinline__ Projected project_gaussian(const PackedCloud& cloud, 
             for (int c = 0; c < 3; c++)
 #pragma unroll
                 for (int r = 0; r < 3; r++) M3(Wm, c, r) = M4(fc.view, c, r);
-            const float4 ca = __ldg(cloud.covA + i), cb = __ldg(cloud.covB + i);
-            float V[9] = {ca.x, ca.y, ca.z, ca.w, cb.x, cb.y, cb.z, cb.w, __ldg(cloud.covC + i)};
+            float V[9] = {ca.x, ca.y, ca.z, ca.w, cb.x, cb.y, cb.z, cb.w, cc};
             float JW[9], JWt[9], Vp[9];
             mat3_mul(J, Wm, JW);
 #pragma unroll
@@ -205,7 +215,7 @@ __device__ __forceinline__ Projected project_gaussian(const PackedCloud& cloud, 
                 const float dx = x - fc.eye[0], dy = y - fc.eye[1], dz = z - fc.eye[2];
                 const float len = sqrtf((dx * dx + dy * dy) + dz * dz);
                 float rgb[3];
-                radiance<SH_MODE>(cloud, i, dx / len, dy / len, dz / len, rgb);
+                radiance<SH_MODE>(cloud, i, dx / len, dy / len, dz / len, rgb, dcPre);
                 if (fc.srgb)
                 {
 #pragma unroll
