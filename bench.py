@@ -58,6 +58,19 @@ def camera_for_rank(name: str, rank: int, world: int) -> np.ndarray:
     from splatapult_b200 import scenes
 
     z = WORKLOADS[name]["cam_z"]
+    if world > 1 and name.startswith("6m"):
+        # BASELINE configs[4]: 8 cameras from a cameras.json (INRIA schema, read by the C++ CamerasConfig), one view per GPU
+        import splatapult_b200 as sp
+        from splatapult_b200 import sharding
+
+        path = os.path.join(SCENE_DIR, "cameras_ring8.json")
+        if not os.path.exists(path):  # written by scene_path() on rank 0 before the other ranks get here
+            scenes.write_cameras_json(path, scenes.ring_cameras(8, z, 3.0), WIDTH, HEIGHT, 1303.7)
+        cfg = sp.CamerasConfig()
+        if not cfg.ImportJson(path):
+            raise RuntimeError(cfg.LastError())
+        mine = sharding.views_for_rank(cfg.GetNumCameras(), rank, world)
+        return cfg.GetCamera(mine[0] if mine else 0)[0]
     if rank == 0:
         return scenes.translate(0, 0, z)
     ang = 2.0 * math.pi * rank / max(world, 1)
@@ -447,6 +460,15 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     if rank == 0:
         scene_path(args.workload)  # generate before anybody needs it
+        if world > 1 and args.workload.startswith("6m"):
+            from splatapult_b200 import scenes
+
+            scenes.write_cameras_json(os.path.join(SCENE_DIR, "cameras_ring8.json"), scenes.ring_cameras(8, WORKLOADS[args.workload]["cam_z"], 3.0),
+                                      WIDTH, HEIGHT, 1303.7)
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.barrier()  # scene and cameras.json exist before any other rank looks for them
     out = run_ours(args, rank, local_rank, world)
     if out is not None:
         print(json.dumps(out), flush=True)

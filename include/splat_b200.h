@@ -154,6 +154,16 @@ enum {
 };
 SPL_API int spl_renderer_tap(spl_renderer*, int what, void* host, size_t bytes);
 
+/* ---------------------------------------------------------------- CamerasConfig (src/camerasconfig.h:12-32) */
+typedef struct spl_cameras spl_cameras;
+SPL_API spl_cameras* spl_cameras_create(void);
+SPL_API void spl_cameras_destroy(spl_cameras*);
+SPL_API int spl_cameras_import_json(spl_cameras*, const char* json_filename);           /* ImportJson :19 */
+SPL_API size_t spl_cameras_count(const spl_cameras*);                                   /* GetNumCameras :22 */
+/* Camera{mat, fov} of GetCameraVec()[index]: camera-to-world column-major float[16] (what Sort/Render take), fov[2] */
+SPL_API int spl_cameras_get(const spl_cameras*, size_t index, float camera_mat[16], float fov[2]);
+SPL_API int spl_cameras_estimate_floor_plane(const spl_cameras*, float normal_out[3], float pos_out[3]); /* :24 */
+
 /* ---------------------------------------------------------------- stand-alone u64|u32 radix sort */
 SPL_API spl_sorter* spl_sorter_create(int device, uint64_t capacity);
 SPL_API void spl_sorter_destroy(spl_sorter*);

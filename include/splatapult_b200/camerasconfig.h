@@ -1,0 +1,32 @@
+// camerasconfig.h -- INRIA cameras.json reader.  Drop-in for the reference's CamerasConfig
+// (src/camerasconfig.h:12-32, src/camerasconfig.cpp:20-95) without nlohmann-json / glm.
+#pragma once
+#include <cstddef>
+#include <string>
+#include <vector>
+
+#include "splatmath.h"
+
+struct Camera
+{
+    splat::mat4 mat;  // inverse view matrix (camera-to-world), the cameraMat SplatRenderer::Sort/Render take
+    splat::vec2 fov;
+};
+
+class CamerasConfig
+{
+public:
+    CamerasConfig() = default;
+
+    bool ImportJson(const std::string& jsonFilename);
+
+    const std::vector<Camera>& GetCameraVec() const { return cameraVec; }
+    size_t GetNumCameras() const { return cameraVec.size(); }
+
+    void EstimateFloorPlane(splat::vec3& normalOut, splat::vec3& posOut) const;
+    const std::string& GetError() const { return error; }
+
+protected:
+    std::vector<Camera> cameraVec;
+    std::string error;
+};

@@ -6,6 +6,7 @@ the parity tests read like calls into the reference.  All compute is in libsplat
 is no CPU fallback -- without the library or without a GPU the renderer raises.
 """
 from .api import (  # noqa: F401
+    CamerasConfig,
     FB_FP16,
     FB_FP32,
     GaussianCloud,

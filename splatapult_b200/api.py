@@ -91,6 +91,12 @@ _SIGNATURES = [
     ("spl_renderer_reserve", C.c_int, [C.c_void_p, C.c_uint64]),
     ("spl_renderer_set_option", C.c_int, [C.c_void_p, C.c_int, C.c_double]),
     ("spl_renderer_tap", C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t]),
+    ("spl_cameras_create", C.c_void_p, []),
+    ("spl_cameras_destroy", None, [C.c_void_p]),
+    ("spl_cameras_import_json", C.c_int, [C.c_void_p, C.c_char_p]),
+    ("spl_cameras_count", C.c_size_t, [C.c_void_p]),
+    ("spl_cameras_get", C.c_int, [C.c_void_p, C.c_size_t, _FP, _FP]),
+    ("spl_cameras_estimate_floor_plane", C.c_int, [C.c_void_p, _FP, _FP]),
     ("spl_sorter_create", C.c_void_p, [C.c_int, C.c_uint64]),
     ("spl_sorter_destroy", None, [C.c_void_p]),
     ("spl_sorter_sort", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_int, C.c_void_p]),
@@ -300,6 +306,40 @@ class SplatRenderer:
         if out.nbytes:
             _check(lib().spl_renderer_tap(self._h, what, out.ctypes.data, out.nbytes))
         return out
+
+
+class CamerasConfig:
+    """Mirror of the reference's CamerasConfig (src/camerasconfig.h:12-32): INRIA cameras.json -> cameraMat list."""
+
+    def __init__(self):
+        self._h = lib().spl_cameras_create()
+        if not self._h:
+            raise MemoryError("spl_cameras_create failed")
+
+    def __del__(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h and _lib is not None:
+            _lib.spl_cameras_destroy(h)
+
+    def ImportJson(self, json_filename: str) -> bool:
+        return lib().spl_cameras_import_json(self._h, os.fsencode(json_filename)) == 0
+
+    def GetNumCameras(self) -> int:
+        return lib().spl_cameras_count(self._h)
+
+    def GetCamera(self, index: int):
+        """(mat float32[16] column-major camera-to-world, fov float32[2]) of GetCameraVec()[index]."""
+        m, f = np.zeros(16, np.float32), np.zeros(2, np.float32)
+        _check(lib().spl_cameras_get(self._h, index, _fptr(m), _fptr(f)))
+        return m, f
+
+    def EstimateFloorPlane(self):
+        n, p = np.zeros(3, np.float32), np.zeros(3, np.float32)
+        _check(lib().spl_cameras_estimate_floor_plane(self._h, _fptr(n), _fptr(p)))
+        return n, p
+
+    def LastError(self) -> str:
+        return (lib().spl_last_error() or b"").decode(errors="replace")
 
 
 def sort_pairs_host(keys: np.ndarray, vals: np.ndarray, begin_bit: int = 0, end_bit: int = 64):

@@ -190,6 +190,41 @@ int spl_renderer_tap(spl_renderer* h, int what, void* host, size_t bytes)
 
 }  // extern "C"
 
+// ------------------------------------------------------------------ cameras.json
+#include "splatapult_b200/camerasconfig.h"
+struct spl_cameras
+{
+    CamerasConfig cfg;
+};
+extern "C" {
+spl_cameras* spl_cameras_create(void) { return new (std::nothrow) spl_cameras; }
+void spl_cameras_destroy(spl_cameras* c) { delete c; }
+int spl_cameras_import_json(spl_cameras* c, const char* path)
+{
+    if (!c || !path) return set_error(SPL_ERR_ARG, "null argument");
+    if (!c->cfg.ImportJson(path)) return set_error(SPL_ERR_IO, c->cfg.GetError());
+    return SPL_OK;
+}
+size_t spl_cameras_count(const spl_cameras* c) { return c ? c->cfg.GetNumCameras() : 0; }
+int spl_cameras_get(const spl_cameras* c, size_t index, float camera_mat[16], float fov[2])
+{
+    if (!c || index >= c->cfg.GetNumCameras()) return set_error(SPL_ERR_ARG, "camera index out of range");
+    const Camera& cam = c->cfg.GetCameraVec()[index];
+    if (camera_mat) std::memcpy(camera_mat, cam.mat.m, sizeof cam.mat.m);
+    if (fov) { fov[0] = cam.fov.x; fov[1] = cam.fov.y; }
+    return SPL_OK;
+}
+int spl_cameras_estimate_floor_plane(const spl_cameras* c, float normal_out[3], float pos_out[3])
+{
+    if (!c || !normal_out || !pos_out) return set_error(SPL_ERR_ARG, "null argument");
+    splat::vec3 n, p;
+    c->cfg.EstimateFloorPlane(n, p);
+    normal_out[0] = n.x; normal_out[1] = n.y; normal_out[2] = n.z;
+    pos_out[0] = p.x; pos_out[1] = p.y; pos_out[2] = p.z;
+    return SPL_OK;
+}
+}  // extern "C"
+
 // ------------------------------------------------------------------ stand-alone sorter
 struct spl_sorter
 {
