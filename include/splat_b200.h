@@ -175,6 +175,11 @@ SPL_API int spl_sorter_sort(spl_sorter*, void* d_keys_in, void* d_vals_in, void*
 SPL_API int spl_sort_pairs_host(const uint64_t* keys, const uint32_t* vals, uint64_t n, int begin_bit, int end_bit,
                                 uint64_t* keys_out, uint32_t* vals_out);
 
+/* egress: write a host copy of the float target as an 8-bit binary PPM ("P6"), top row first, values
+ * clamped to [0,1] like the reference's default RGBA8 window target (the 1:1 blit of src/app.cpp:1076-1082,
+ * shader/desktop_frag.glsl:32-37).  fb_format tells whether `host_fb` holds float4 or half4 pixels (row 0 = bottom). */
+SPL_API int spl_write_ppm(const char* path, const void* host_fb, int width, int height, int fb_format);
+
 /* pinned host memory for the end-to-end path */
 SPL_API void* spl_host_alloc(size_t bytes);
 SPL_API void spl_host_free(void*);

@@ -18,6 +18,7 @@ from .api import (  # noqa: F401
     lib,
     library_path,
     sort_pairs_host,
+    write_ppm,
 )
 from .scenes import (  # noqa: F401
     FOVY,

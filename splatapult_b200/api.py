@@ -101,6 +101,7 @@ _SIGNATURES = [
     ("spl_sorter_destroy", None, [C.c_void_p]),
     ("spl_sorter_sort", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_int, C.c_void_p]),
     ("spl_sort_pairs_host", C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
+    ("spl_write_ppm", C.c_int, [C.c_char_p, C.c_void_p, C.c_int, C.c_int, C.c_int]),
     ("spl_host_alloc", C.c_void_p, [C.c_size_t]),
     ("spl_host_free", None, [C.c_void_p]),
 ]
@@ -349,6 +350,14 @@ def sort_pairs_host(keys: np.ndarray, vals: np.ndarray, begin_bit: int = 0, end_
     ko, vo = np.empty_like(keys), np.empty_like(vals)
     _check(lib().spl_sort_pairs_host(keys.ctypes.data, vals.ctypes.data, len(keys), begin_bit, end_bit, ko.ctypes.data, vo.ctypes.data))
     return ko, vo
+
+
+def write_ppm(path: str, fb: np.ndarray) -> None:
+    """8-bit binary PPM of a framebuffer [H, W, 4] float32 / float16 (row 0 = bottom); top row first, clamped to [0,1]."""
+    fb = np.ascontiguousarray(fb)
+    if fb.ndim != 3 or fb.shape[2] != 4 or fb.dtype not in (np.float32, np.float16):
+        raise ValueError("expected [H, W, 4] float32 or float16")
+    _check(lib().spl_write_ppm(os.fsencode(path), fb.ctypes.data, fb.shape[1], fb.shape[0], FB_FP16 if fb.dtype == np.float16 else FB_FP32))
 
 
 class _Pinned:

@@ -1,8 +1,12 @@
 // capi.cu -- extern "C" surface of libsplat_b200.so (include/splat_b200.h): plain handles over the C++ classes.
+#include <cuda_fp16.h>
+
+#include <cstdio>
 #include <cstring>
 #include <memory>
 #include <new>
 #include <string>
+#include <vector>
 
 #include "kernels.h"
 #include "splat_b200.h"
@@ -343,6 +347,37 @@ int spl_sort_pairs_host(const uint64_t* keys, const uint32_t* vals, uint64_t n, 
     cudaFree(dk0); cudaFree(dk1); cudaFree(dv0); cudaFree(dv1);
     spl_sorter_destroy(s);
     return rc;
+}
+
+int spl_write_ppm(const char* path, const void* host_fb, int width, int height, int fb_format)
+{
+    if (!path || !host_fb || width <= 0 || height <= 0) return set_error(SPL_ERR_ARG, "bad argument");
+    FILE* f = std::fopen(path, "wb");
+    if (!f) return set_error(SPL_ERR_IO, std::string("failed to open ") + path);
+    std::fprintf(f, "P6\n%d %d\n255\n", width, height);
+    std::vector<unsigned char> row((size_t)width * 3);
+    auto to8 = [](float v) { v = v < 0.0f ? 0.0f : (v > 1.0f ? 1.0f : v); return (unsigned char)(v * 255.0f + 0.5f); };
+    for (int y = height - 1; y >= 0; y--)  // the framebuffer is bottom-up, images are top-down
+    {
+        for (int x = 0; x < width; x++)
+        {
+            float rgb[3];
+            if (fb_format == SPL_FB_FP16)
+            {
+                const __half* p = static_cast<const __half*>(host_fb) + ((size_t)y * width + x) * 4;
+                for (int c = 0; c < 3; c++) rgb[c] = __half2float(p[c]);
+            }
+            else
+            {
+                const float* p = static_cast<const float*>(host_fb) + ((size_t)y * width + x) * 4;
+                for (int c = 0; c < 3; c++) rgb[c] = p[c];
+            }
+            for (int c = 0; c < 3; c++) row[(size_t)x * 3 + c] = to8(rgb[c]);
+        }
+        std::fwrite(row.data(), 1, row.size(), f);
+    }
+    std::fclose(f);
+    return SPL_OK;
 }
 
 void* spl_host_alloc(size_t bytes)
