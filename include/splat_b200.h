@@ -110,6 +110,9 @@ SPL_API int spl_renderer_read_framebuffer_async(spl_renderer*, void* host, size_
 SPL_API int spl_renderer_read_framebuffer(spl_renderer*, void* host, size_t bytes);
 /* device-side join: the render stream waits for every framebuffer copy still in flight (no host block) */
 SPL_API int spl_renderer_fence_copies(spl_renderer*);
+/* host-side wait: returns when at most keep_in_flight (0 or 1) async framebuffer copies are still pending; with 1,
+ * the previous frame's pixels are in host memory while the current frame's copy is still running */
+SPL_API int spl_renderer_wait_copies(spl_renderer*, int keep_in_flight);
 /* host waits for the render stream and the copy stream */
 SPL_API int spl_renderer_synchronize(spl_renderer*);
 

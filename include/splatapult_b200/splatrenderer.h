@@ -46,6 +46,7 @@ public:
     bool ReadFramebufferAsync(void* host, size_t bytes);
     bool ReadFramebuffer(void* host, size_t bytes);  // waits; transparently re-renders once on capacity overflow
     bool FenceCopies();   // make the render stream wait (device-side) for every copy still in flight
+    bool WaitCopies(int keepInFlight = 0);  // host waits until at most keepInFlight (0|1) async copies are pending
     bool Synchronize();   // host waits for the render stream and the copy stream
     bool GetStats(spl_stats* out);
     bool Reserve(uint64_t instanceCapacity);

@@ -86,6 +86,7 @@ _SIGNATURES = [
     ("spl_renderer_read_framebuffer_async", C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
     ("spl_renderer_read_framebuffer", C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
     ("spl_renderer_fence_copies", C.c_int, [C.c_void_p]),
+    ("spl_renderer_wait_copies", C.c_int, [C.c_void_p, C.c_int]),
     ("spl_renderer_synchronize", C.c_int, [C.c_void_p]),
     ("spl_renderer_stats", C.c_int, [C.c_void_p, C.POINTER(Stats)]),
     ("spl_renderer_reserve", C.c_int, [C.c_void_p, C.c_uint64]),
@@ -277,6 +278,10 @@ class SplatRenderer:
     def FenceCopies(self) -> None:
         """device-side join: the render stream waits for every framebuffer copy still in flight."""
         _check(lib().spl_renderer_fence_copies(self._h))
+
+    def WaitCopies(self, keep_in_flight: int = 0) -> None:
+        """host-side wait until at most keep_in_flight (0 or 1) asynchronous framebuffer copies are pending."""
+        _check(lib().spl_renderer_wait_copies(self._h, int(keep_in_flight)))
 
     def Synchronize(self) -> None:
         _check(lib().spl_renderer_synchronize(self._h))

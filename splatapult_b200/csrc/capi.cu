@@ -166,6 +166,11 @@ int spl_renderer_fence_copies(spl_renderer* h)
     if (!h) return set_error(SPL_ERR_ARG, "null argument");
     return from_renderer(h, h->r.FenceCopies());
 }
+int spl_renderer_wait_copies(spl_renderer* h, int keep_in_flight)
+{
+    if (!h) return set_error(SPL_ERR_ARG, "null argument");
+    return from_renderer(h, h->r.WaitCopies(keep_in_flight));
+}
 int spl_renderer_synchronize(spl_renderer* h)
 {
     if (!h) return set_error(SPL_ERR_ARG, "null argument");

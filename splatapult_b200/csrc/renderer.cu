@@ -417,6 +417,26 @@ struct RendererImpl
         return ok();
     }
 
+    // block the HOST until at most `keepInFlight` (0 or 1) framebuffer copies are still pending; with 1, the copy
+    // of the frame before the current one has landed, so a consumer can process it while this frame's copy runs
+    int waitCopies(int keepInFlight)
+    {
+        if (int rc = begin()) return rc;
+        if (keepInFlight < 0 || keepInFlight > 1) return fail(SPL_ERR_ARG, "keep_in_flight must be 0 or 1");
+        const int older = fbCur ^ 1;
+        if (copyPending[older])
+        {
+            CU_TRY(cudaEventSynchronize(evCopied[older]));
+            copyPending[older] = false;
+        }
+        if (keepInFlight == 0 && copyPending[fbCur])
+        {
+            CU_TRY(cudaEventSynchronize(evCopied[fbCur]));
+            copyPending[fbCur] = false;
+        }
+        return ok();
+    }
+
     int readCounters(FrameCounters* out)
     {
         CU_TRY(cudaMemcpyAsync(out, dCtr, sizeof(FrameCounters), cudaMemcpyDeviceToHost, stream));
@@ -607,6 +627,8 @@ bool SplatRenderer::Synchronize()
 }
 
 bool SplatRenderer::FenceCopies() { FORWARD(impl->fenceCopies()); }
+
+bool SplatRenderer::WaitCopies(int keepInFlight) { FORWARD(impl->waitCopies(keepInFlight)); }
 
 bool SplatRenderer::GetStats(spl_stats* out) { FORWARD(impl->stats(out)); }
 

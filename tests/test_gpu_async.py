@@ -40,6 +40,37 @@ def test_overlapped_readback_matches_blocking_reads(splat, golden_dir):
         np.testing.assert_array_equal(got, want[k % 3])
 
 
+def test_wait_copies_streams_previous_frame_to_the_host(splat, golden_dir):
+    """Consumer pattern of INTEGRATION.md: after frame k's async copy is enqueued, WaitCopies(1) guarantees frame
+    k-1's pixels are in host memory (host-side wait, no stream synchronise)."""
+    g = np.load(os.path.join(golden_dir, "synth_2k_deg3_320x180.npz"))
+    gc = splat.GaussianCloud()
+    gc.SetRawData(g["aos"], True)
+    r = splat.SplatRenderer()
+    assert r.Init(gc, False, False)
+    vp = [0, 0, 320, 180]
+    cams = [g["camera"], scenes.translate(0.7, -0.3, 9.0), scenes.translate(-1.0, 0.4, 11.0)]
+    want = []
+    for c in cams:
+        r.Render(c, g["proj"], vp, NF)
+        want.append(r.ReadFramebuffer().copy())
+    nbytes = 320 * 180 * 16
+    pinned = [splat.host_alloc(nbytes) for _ in range(2)]
+    for p in pinned:
+        p.array(np.float32, (180, 320, 4))[:] = -1.0
+    for k in range(7):
+        r.Sort(cams[k % 3], g["proj"], vp, NF)
+        r.Render(cams[k % 3], g["proj"], vp, NF)
+        r.ReadFramebufferAsync(pinned[k & 1].ptr, nbytes)
+        r.WaitCopies(1)
+        if k > 0:
+            np.testing.assert_array_equal(pinned[(k - 1) & 1].array(np.float32, (180, 320, 4)), want[(k - 1) % 3])
+    r.WaitCopies(0)
+    np.testing.assert_array_equal(pinned[0].array(np.float32, (180, 320, 4)), want[0])
+    with pytest.raises(api.SplatError):
+        r.WaitCopies(2)
+
+
 def test_fp16_async_and_resolution_change(splat, golden_dir):
     g = np.load(os.path.join(golden_dir, "synth_2k_deg3_320x180.npz"))
     gc = splat.GaussianCloud()
