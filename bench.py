@@ -204,6 +204,7 @@ def run_ours(args, rank, local_rank, world):
 
     r.SetOption(api.OPT_SORT_MODE, {"lsd": api.SORT_LSD, "lsd_flat": api.SORT_LSD_FLAT, "binned": api.SORT_BINNED}[args.sort_mode])
     r.SetOption(api.OPT_SORT_TILE, args.sort_tile)
+    r.SetOption(api.OPT_SUBBLOCK_CULL, args.subblock_cull)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
 
     def frame():
@@ -435,6 +436,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--sort-mode", default="lsd", choices=["binned", "lsd", "lsd_flat"])
     ap.add_argument("--sort-tile", type=int, default=4096, choices=[2048, 4096])
+    ap.add_argument("--subblock-cull", type=int, default=2, choices=[0, 1, 2], help="compositor sub-block mask: 0 none, 1 box, 2 exact ellipse")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))

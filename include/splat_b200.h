@@ -138,7 +138,9 @@ enum {
     SPL_OPT_PROFILE = 1,      /* 1: bracket stages with CUDA events (stage_ms) */
     SPL_OPT_INSTANCES_PER_GAUSSIAN = 2, /* initial capacity factor, before init (default 16) */
     SPL_OPT_SORT_TILE = 4,    /* keys per onesweep tile: 4096 (default) or 2048 */
-    SPL_OPT_SORT_MODE = 3     /* SPL_SORT_LSD (default) or SPL_SORT_BINNED; both give bit-identical tile lists */
+    SPL_OPT_SORT_MODE = 3,    /* SPL_SORT_LSD (default), SPL_SORT_LSD_FLAT or SPL_SORT_BINNED; all give bit-identical tile lists */
+    SPL_OPT_SUBBLOCK_CULL = 5 /* compositor's per-entry 8x4 sub-block mask: 0 none, 1 footprint box, 2 exact ellipse (default);
+                                 culling only skips lanes whose weight is discarded anyway: images are bit-identical */
 };
 enum {
     SPL_SORT_BINNED = 0, /* MSD: counting sort on the tile id, then per-tile shared-memory sort of (depthKey, id) */

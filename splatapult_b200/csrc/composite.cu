@@ -74,7 +74,7 @@ struct CompSmem
 template <bool HALF>
 __global__ void __launch_bounds__(kCompThreads, 6)
 k_composite(const uint2* __restrict__ ranges, const uint32_t* __restrict__ vals, int idStride, const ProjRecord* __restrict__ rec,
-            void* __restrict__ fb, int width, int height, int tilesX, float earlyOutT)
+            void* __restrict__ fb, int width, int height, int tilesX, float earlyOutT, int cullMode)
 {
     __shared__ CompSmem s;
 
@@ -108,37 +108,83 @@ k_composite(const uint2* __restrict__ ranges, const uint32_t* __restrict__ vals,
         }
     };
     auto stage = [&](int buf) {
-        if (!have) return;
+        // a warp evaluates its hits highest ballot bit first (FLO, no bit reversal): each group of 32 entries is
+        // stored in reverse lane order, so the highest bit is the nearest entry
+        const int sidx = tid ^ 31;
+        if (!have)
+        {
+            s.mask[buf][sidx] = 0u;
+            return;
+        }
         const float kLog2e = 1.4426950408889634f;
         const float h = -0.5f * kLog2e;
-        s.a[buf][tid] = make_float4(q0.x, q0.y, h * q0.z, h * (q0.w + q1.x));
-        s.b[buf][tid] = make_float4(h * q1.y, log2f(q2.y), q1.z, q1.w);
-        s.c[buf][tid] = make_float4(q2.x, 0.0f, 0.0f, 0.0f);
-        // footprint box inside this tile -> sub-block mask.  Same bound as the projection kernel's tile
-        // rectangle: {alpha exp(-Q/2) > 1/256} lies within |dx| <= sqrt(r2 Sxx), |dy| <= sqrt(r2 Syy),
-        // r2 = 2 ln(256 alpha); Sigma = (Sigma^-1)^-1; inflated so rounding cannot drop a contributing pixel.
-        const float det = q0.z * q1.y - q0.w * q1.x;
-        const float r2 = 2.0f * 0.6931471805599453f * (8.0f + __log2f(q2.y));
-        const float rdet = __fdividef(r2, det);
-        const float ex = sqrtf(fmaxf(rdet * q1.y, 0.0f)) * 1.002f + 0.02f;
-        const float ey = sqrtf(fmaxf(rdet * q0.z, 0.0f)) * 1.002f + 0.02f;
-        // pixel centres (x + 0.5) in [px - ex, px + ex], relative to the tile origin
-        const float lx0 = q0.x - ex - 0.5f - tileX0, lx1 = q0.x + ex - 0.5f - tileX0;
-        const float ly0 = q0.y - ey - 0.5f - tileY0, ly1 = q0.y + ey - 0.5f - tileY0;
+        s.a[buf][sidx] = make_float4(q0.x, q0.y, h * q0.z, h * (q0.w + q1.x));
+        s.b[buf][sidx] = make_float4(h * q1.y, log2f(q2.y), q1.z, q1.w);
+        s.c[buf][sidx] = make_float4(q2.x, 0.0f, 0.0f, 0.0f);
+        // Sub-block mask: which 8x4 pixel blocks can hold a pixel with alpha exp(-Q/2) > 1/256, i.e. a pixel centre
+        // inside the ellipse Q(d) = A dx^2 + 2B dx dy + C dy^2 < r2, r2 = 2 ln(256 alpha) (inflated so rounding in
+        // the evaluation below cannot put a contributing pixel outside).  A culled lane would have been discarded
+        // anyway (tw = 0 leaves the accumulators bit-unchanged): the image does not depend on the mask.
+        const float A = q0.z, B = 0.5f * (q0.w + q1.x), Cc = q1.y;
+        // det = A C - B^2 by Kahan's difference of products: elongated splats cancel almost completely
+        const float bb = B * B;
+        const float det = fmaf(A, Cc, -bb) + fmaf(-B, B, bb);
+        const float r2 = 2.0f * 0.6931471805599453f * (8.0f + __log2f(q2.y)) * 1.002f + 0.004f;
         uint32_t m = 0xffu;
-        if (lx0 == lx0 && lx1 == lx1 && ly0 == ly0 && ly1 == ly1)  // NaN extents: evaluate everywhere
+        // not a bounded ellipse as stored (or NaN): evaluate everywhere
+        if (cullMode != 0 && det > 0.0f && A > 0.0f && r2 == r2 && fabsf(q0.x) < 1e30f && fabsf(q0.y) < 1e30f)
         {
-            const int px0 = (int)fmaxf(ceilf(lx0), 0.0f), px1 = (int)fminf(floorf(lx1), (float)(kTileSize - 1));
-            const int py0 = (int)fmaxf(ceilf(ly0), 0.0f), py1 = (int)fminf(floorf(ly1), (float)(kTileSize - 1));
             m = 0u;
-            if (px1 >= px0 && py1 >= py0)
+            if (r2 > 0.0f)
             {
-                const int c0 = px0 / kSubW, c1 = px1 / kSubW, r0 = py0 / kSubH, r1 = py1 / kSubH;
-                const uint32_t colBits = ((1u << (c1 - c0 + 1)) - 1u) << c0;
-                for (int r = r0; r <= r1; r++) m |= colBits << (r * kSubCols);
+                const float eps = 0.01f;
+                const float rdet = __fdividef(r2, det);
+                const float ex = sqrt_approx(rdet * Cc) * 1.001f, ey = sqrt_approx(rdet * A) * 1.001f;  // half extents
+                const float ox = tileX0 - q0.x, oy = tileY0 - q0.y;  // tile origin relative to the splat centre
+                if (cullMode == 1)
+                {
+                    // footprint box only
+                    for (int r = 0; r < kSubRows; r++)
+                    {
+                        const float d0 = oy + (float)(r * kSubH) + 0.5f, d1 = d0 + (float)(kSubH - 1);
+                        if (d0 - eps > ey || d1 + eps < -ey) continue;
+                        for (int c = 0; c < kSubCols; c++)
+                        {
+                            const float c0 = ox + (float)(c * kSubW) + 0.5f, c1 = c0 + (float)(kSubW - 1);
+                            if (c0 - eps <= ex && c1 + eps >= -ex) m |= 1u << (r * kSubCols + c);
+                        }
+                    }
+                }
+                else
+                {
+                    // exact: the ellipse cut by the row band dy in [d0, d1] is convex, so it meets a block iff its
+                    // x-extent [xl, xr] over the band overlaps the block's columns.  x_right(dy) = -(B/A) dy +
+                    // sqrt(r2 A - det dy^2)/A is concave with its maximum at the ellipse's rightmost point
+                    // dy* = -(B/C) ex: clamp dy* into the band and evaluate; x_left mirrors it.
+                    const float rA = __fdividef(1.0f, A);
+                    const float slope = -B * rA;
+                    const float tStar = -B * __fdividef(ex, Cc);
+                    const float r2A = r2 * A * 1.002f;
+#pragma unroll
+                    for (int r = 0; r < kSubRows; r++)
+                    {
+                        const float d0 = oy + (float)(r * kSubH) + 0.5f - eps, d1 = d0 + (float)(kSubH - 1) + 2.0f * eps;
+                        const float lo = fmaxf(d0, -ey), hi = fminf(d1, ey);
+                        if (lo > hi) continue;
+                        const float tr = fminf(fmaxf(tStar, lo), hi), tl = fminf(fmaxf(-tStar, lo), hi);
+                        const float xr = fmaf(slope, tr, sqrt_approx(fmaxf(fmaf(-det * tr, tr, r2A), 0.0f)) * rA) + eps;
+                        const float xl = fmaf(slope, tl, -sqrt_approx(fmaxf(fmaf(-det * tl, tl, r2A), 0.0f)) * rA) - eps;
+#pragma unroll
+                        for (int c = 0; c < kSubCols; c++)
+                        {
+                            const float c0 = ox + (float)(c * kSubW) + 0.5f, c1 = c0 + (float)(kSubW - 1);
+                            if (c0 <= xr && c1 >= xl) m |= 1u << (r * kSubCols + c);
+                        }
+                    }
+                }
             }
         }
-        s.mask[buf][tid] = m;
+        s.mask[buf][sidx] = m;
     };
 
     uint32_t hi = range.y;
@@ -157,14 +203,24 @@ k_composite(const uint2* __restrict__ ranges, const uint32_t* __restrict__ vals,
         {
             for (uint32_t base = 0; base < cnt; base += 32)
             {
-                const uint32_t m = (base + lane < cnt) ? s.mask[buf][base + lane] : 0u;
+                const uint32_t m = s.mask[buf][base + lane];  // slots past the list's end hold 0
                 uint32_t hits = __ballot_sync(0xffffffffu, (m >> warp) & 1u);
+                const uint32_t groupAddr = (uint32_t)__cvta_generic_to_shared(&s.a[buf][base]);
                 while (hits)
                 {
-                    const uint32_t j = base + __ffs(hits) - 1;
-                    hits &= hits - 1;
-                    const float4 a = s.a[buf][j], b = s.b[buf][j];
-                    const float blue = s.c[buf][j].x;
+                    // 23-instruction body: FLO, BMSK, LOP3, IMAD for the walk; 3 LDS; 15 FP32/MUFU; BRA
+                    uint32_t top, below;
+                    asm("bfind.u32 %0, %1;" : "=r"(top) : "r"(hits));                       // index of the highest set bit
+                    asm("bmsk.clamp.b32 %0, %1, %2;" : "=r"(below) : "r"(0), "r"(top));   // bits [0, top)
+                    hits &= below;
+                    const uint32_t addr = groupAddr + top * 16u;
+                    float4 a, b;
+                    float blue;
+                    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w) : "r"(addr));
+                    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4+%5];"
+                                 : "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w)
+                                 : "r"(addr), "n"(sizeof(CompSmem::a)));
+                    asm volatile("ld.shared.f32 %0, [%1+%2];" : "=f"(blue) : "r"(addr), "n"(sizeof(CompSmem::a) + sizeof(CompSmem::b)));
                     const float dx = fx - a.x, dy = fy - a.y;
                     const float pw = fmaf(dx, fmaf(a.z, dx, a.w * dy), fmaf(b.x * dy, dy, b.y));
                     const float w = ex2_approx(pw);
@@ -200,14 +256,14 @@ k_composite(const uint2* __restrict__ ranges, const uint32_t* __restrict__ vals,
 }
 
 cudaError_t launch_composite(const uint2* ranges, const uint32_t* sortedVals, int idStrideWords, const ProjRecord* rec, void* framebuffer,
-                             int fbFormat, int width, int height, int tilesX, int tilesY, float earlyOutT, cudaStream_t stream)
+                             int fbFormat, int width, int height, int tilesX, int tilesY, float earlyOutT, int cullMode, cudaStream_t stream)
 {
     const int tiles = tilesX * tilesY;
     if (tiles <= 0) return cudaSuccess;
     if (fbFormat == 1)
-        k_composite<true><<<tiles, kCompThreads, 0, stream>>>(ranges, sortedVals, idStrideWords, rec, framebuffer, width, height, tilesX, earlyOutT);
+        k_composite<true><<<tiles, kCompThreads, 0, stream>>>(ranges, sortedVals, idStrideWords, rec, framebuffer, width, height, tilesX, earlyOutT, cullMode);
     else
-        k_composite<false><<<tiles, kCompThreads, 0, stream>>>(ranges, sortedVals, idStrideWords, rec, framebuffer, width, height, tilesX, earlyOutT);
+        k_composite<false><<<tiles, kCompThreads, 0, stream>>>(ranges, sortedVals, idStrideWords, rec, framebuffer, width, height, tilesX, earlyOutT, cullMode);
     return cudaGetLastError();
 }
 

@@ -163,6 +163,14 @@ __device__ __forceinline__ float ex2_approx(float x)
     return y;
 }
 
+// MUFU.SQRT (max relative error 2^-23 over the normal range): for conservative bounds that are inflated anyway
+__device__ __forceinline__ float sqrt_approx(float x)
+{
+    float y;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
 __device__ __forceinline__ uint32_t lanemask_lt()
 {
     uint32_t m;

@@ -74,6 +74,6 @@ cudaError_t launch_tile_ranges(const unsigned long long* sortedKeys, const uint3
 // ids: gaussian id of list entry k is ids[k * idStrideWords] (1: u32 payload array of the LSD sort, 2: low word of the
 // binned sort's u64 (depthKey << 32 | id) pairs)
 cudaError_t launch_composite(const uint2* ranges, const uint32_t* ids, int idStrideWords, const ProjRecord* rec, void* framebuffer, int fbFormat,
-                             int width, int height, int tilesX, int tilesY, float earlyOutT, cudaStream_t stream);
+                             int width, int height, int tilesX, int tilesY, float earlyOutT, int cullMode, cudaStream_t stream);
 
 }  // namespace splat

@@ -36,6 +36,7 @@ struct RendererImpl
     bool ownStream = false;
     int numSMs = 148;
     double earlyOutT = 1e-4;
+    int subblockCull = 2;
     bool profile = false;
     double instancesPerGaussian = 16.0;
     int sortMode = SPL_SORT_LSD;
@@ -400,7 +401,7 @@ struct RendererImpl
         fbW = fc.width; fbH = fc.height;
         if (profile) CU_TRY(cudaEventRecord(ev[4], stream));
         const bool binned = frameSortMode == SPL_SORT_BINNED;
-        CU_TRY(launch_composite(dRanges, binned ? reinterpret_cast<const uint32_t*>(dKeysA) : sortedVals(), binned ? 2 : 1, dRec, dFb, fbFormat, fc.width, fc.height, fc.tilesX, fc.tilesY, (float)earlyOutT, stream));
+        CU_TRY(launch_composite(dRanges, binned ? reinterpret_cast<const uint32_t*>(dKeysA) : sortedVals(), binned ? 2 : 1, dRec, dFb, fbFormat, fc.width, fc.height, fc.tilesX, fc.tilesY, (float)earlyOutT, subblockCull, stream));
         launches += 1;
         if (profile) CU_TRY(cudaEventRecord(ev[5], stream));
         CU_TRY(cudaEventRecord(evRendered[target], stream));
@@ -653,6 +654,10 @@ bool SplatRenderer::SetOption(int option, double value)
         if (value != SPL_SORT_BINNED && value != SPL_SORT_LSD && value != SPL_SORT_LSD_FLAT) { status = SPL_ERR_ARG; error = "unknown sort mode"; return false; }
         impl->sortMode = (int)value;
         impl->haveSort = false;
+        break;
+    case SPL_OPT_SUBBLOCK_CULL:
+        if (value != 0 && value != 1 && value != 2) { status = SPL_ERR_ARG; error = "sub-block cull mode must be 0, 1 or 2"; return false; }
+        impl->subblockCull = (int)value;
         break;
     default: status = SPL_ERR_ARG; error = "unknown option"; return false;
     }
