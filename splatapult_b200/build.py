@@ -62,7 +62,9 @@ def _deps_hash(extra: list[str]) -> str:
 def build(force: bool = False, verbose: bool = False) -> str:
     os.makedirs(OBJ, exist_ok=True)
     stamp = os.path.join(OBJ, "stamp")
-    digest = _deps_hash([])
+    # diagnostic build: SPL_BUILD_DEFINES="SPL_SORT_TIMELINE" adds -D flags (see radix_sort.cu); never set by default
+    defines = ["-D" + d for d in os.environ.get("SPL_BUILD_DEFINES", "").split() if d]
+    digest = _deps_hash(defines)
     if not force and os.path.exists(LIB) and os.path.exists(stamp) and open(stamp).read() == digest:
         return LIB
     nvcc = _nvcc()
@@ -70,7 +72,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     log = []
     for src, extra in CU_SOURCES.items():
         o = os.path.join(OBJ, src + ".o")
-        cmd = [nvcc] + ARCH + NVCC_COMMON + extra + ["-c", os.path.join(CSRC, src), "-o", o]
+        cmd = [nvcc] + ARCH + NVCC_COMMON + extra + defines + ["-c", os.path.join(CSRC, src), "-o", o]
         r = subprocess.run(cmd, capture_output=True, text=True)
         log.append(f"$ {' '.join(cmd)}\n{r.stdout}{r.stderr}")
         if r.returncode:

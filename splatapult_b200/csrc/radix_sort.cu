@@ -17,6 +17,9 @@
 //     shared memory so global stores are digit-run coalesced;
 //   * look-back words carry a 16-bit generation, so nothing is cleared between sorts; element counts are read
 //     from device memory: no host round trip anywhere.
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
 #include "device_common.cuh"
 #include "kernels.h"
 
@@ -31,6 +34,9 @@ __host__ __device__ __forceinline__ uint32_t digit_mask(int shift, int endBit)
     const int bits = endBit - shift;
     return bits >= kRadixBits ? (uint32_t)(kRadixSize - 1) : ((1u << bits) - 1u);
 }
+
+// below this effective number of digit values (1 / sum of squared bin fractions) a pass ranks with MATCH.ANY
+constexpr int kMatchAnyMaxValues = 4;
 
 // look-back status word: [63:62] flag, [47:32] generation, [31:0] count
 constexpr unsigned long long kStAggregate = 1ull << 62;
@@ -111,20 +117,40 @@ struct SortSmem
     unsigned long long keys[kTile];               // TMA destination; reused for the digit-ordered tile
     uint32_t vals[kTile];                         // TMA destination; reused for the digit-ordered payloads
     uint32_t warpCount[kWarps][kRadixSize];       // per-warp digit counters -> exclusive prefix over warps
+    uint32_t matchMask[kWarps][kRadixSize];       // atomic-OR matching: lanes of the warp holding each digit (zero between rows)
     uint32_t ctaExcl[kRadixSize];                 // first local slot of each digit
     uint32_t globalBase[kRadixSize];              // global index of local slot 0 of each digit (minus ctaExcl)
     uint32_t nextHist[kRadixSize];                // histogram of the next pass's digit over this CTA's tiles
     uint32_t scanTmp[kWarps];
+    float sqTmp[kWarps];
     uint32_t tile;
     uint64_t bar;
 };
+
+// SPL_SORT_TIMELINE (diagnostic builds only: `SPL_BUILD_DEFINES=SPL_SORT_TIMELINE python -m splatapult_b200.build`):
+// thread 0 of every CTA stamps %globaltimer at each phase boundary of each tile; with the environment variable
+// SPL_SORT_TIMELINE=<path> set at run time launch_passes_t dumps the stamps; benchmarks/tl_analyze.py reads them.
+#ifdef SPL_SORT_TIMELINE
+#define TLREC(k)                                                          \
+    do                                                                    \
+    {                                                                     \
+        if (tl && tid == 0)                                               \
+        {                                                                 \
+            unsigned long long t_;                                        \
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_));        \
+            tl[(size_t)tile * 8 + (k)] = t_;                              \
+        }                                                                 \
+    } while (0)
+#else
+#define TLREC(k) ((void)0)
+#endif
 
 template <int KPT>
 __global__ void __launch_bounds__(kSortThreads, KPT == 16 ? 3 : 5)
 k_sort_onesweep(const unsigned long long* __restrict__ keysIn, const uint32_t* __restrict__ valsIn, unsigned long long* __restrict__ keysOut,
                 uint32_t* __restrict__ valsOut, const uint32_t* __restrict__ nDevice, int shift, uint32_t mask, int nextShift, uint32_t nextMask,
                 const uint32_t* __restrict__ histogram, uint32_t* __restrict__ histogramNext, unsigned long long* __restrict__ status,
-                uint32_t* __restrict__ ticket, uint32_t gen)
+                uint32_t* __restrict__ ticket, uint32_t gen, unsigned long long* tl)
 {
     using Smem = SortSmem<KPT>;
     constexpr int kTile = Smem::kTile;
@@ -139,8 +165,11 @@ k_sort_onesweep(const unsigned long long* __restrict__ keysIn, const uint32_t* _
 
     // global exclusive scan of this pass's digit histogram: thread d owns digit d
     uint32_t digitStart;
+    bool concentrated;
+    bool digitUsed;  // no key of this pass has digit `tid`: nobody needs its offsets, so it takes no part in the look-back
     {
         const uint32_t h = histogram[tid];
+        digitUsed = h != 0;
         uint32_t incl = h;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1)
@@ -148,8 +177,15 @@ k_sort_onesweep(const unsigned long long* __restrict__ keysIn, const uint32_t* _
             const uint32_t v = __shfl_up_sync(0xffffffffu, incl, d);
             if (lane >= d) incl += v;
         }
+        // sum of squared bin fractions = 1 / (effective number of digit values): decides the matching method below
+        float sq = (float)h * (float)h;
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, d);
         if (lane == 31) s.scanTmp[warp] = incl;
+        if (lane == 0) s.sqTmp[warp] = sq;
         s.nextHist[tid] = 0;
+#pragma unroll
+        for (int w = 0; w < kWarps; w++) s.matchMask[w][tid] = 0;
         if (tid == 0)
         {
             mbar_init(&s.bar, 1);
@@ -157,10 +193,15 @@ k_sort_onesweep(const unsigned long long* __restrict__ keysIn, const uint32_t* _
         }
         __syncthreads();
         uint32_t base = 0;
+        float sqAll = 0.0f;
 #pragma unroll
         for (int w = 0; w < kWarps; w++)
+        {
             if (w < warp) base += s.scanTmp[w];
+            sqAll += s.sqTmp[w];
+        }
         digitStart = base + incl - h;
+        concentrated = sqAll * (float)kMatchAnyMaxValues > (float)n * (float)n;  // effective values < kMatchAnyMaxValues
         __syncthreads();
     }
 
@@ -174,6 +215,7 @@ k_sort_onesweep(const unsigned long long* __restrict__ keysIn, const uint32_t* _
         const uint32_t tile = s.tile;
         if (tile >= numTiles) break;
         const uint32_t nValid = min((uint32_t)kTile, n - tile * kTile);
+        TLREC(0);
 
         if (tid == 0)
         {
@@ -185,6 +227,7 @@ k_sort_onesweep(const unsigned long long* __restrict__ keysIn, const uint32_t* _
         }
         mbar_wait(&s.bar, parity);
         parity ^= 1;
+        TLREC(1);
 
         // ---- rank: warp w owns items [w*KPT*32, (w+1)*KPT*32), item j of a lane = base + j*32 + lane (memory order)
         unsigned long long key[KPT];
@@ -195,21 +238,52 @@ k_sort_onesweep(const unsigned long long* __restrict__ keysIn, const uint32_t* _
             const uint32_t idx = warp * (KPT * 32) + j * 32 + lane;
             key[j] = idx < nValid ? s.keys[idx] : ~0ull;  // padding sorts last inside the tile and is never written
         }
-#pragma unroll
-        for (int j = 0; j < KPT; j++)
+        // peers = lanes of the warp holding the same digit.  Two ways to get it, chosen per pass from the digit
+        // histogram (CTA-uniform): MATCH.ANY iterates over the distinct values in the warp (measured per 4096-key
+        // tile: 1 us when the digit is constant, 7-10 us when it is spread); an atomic OR of the lane bit into a
+        // per-warp, per-digit mask word is conflict-free on spread digits (2.4 us) but serialises when all lanes hit
+        // one word (3.6 us).
+        if (concentrated)
         {
-            const uint32_t d = digit_of(key[j], shift, mask);
-            const uint32_t peers = __match_any_sync(0xffffffffu, d);
-            const uint32_t before = __popc(peers & lanemask_lt());
-            const uint32_t prev = s.warpCount[warp][d];
-            __syncwarp();
-            if (before == 0) s.warpCount[warp][d] = prev + __popc(peers);
-            __syncwarp();
-            pos[j] = (uint16_t)(prev + before);
+#pragma unroll
+            for (int j = 0; j < KPT; j++)
+            {
+                const uint32_t d = digit_of(key[j], shift, mask);
+                const uint32_t peers = __match_any_sync(0xffffffffu, d);
+                const uint32_t before = __popc(peers & lanemask_lt());
+                const uint32_t prev = s.warpCount[warp][d];
+                __syncwarp();
+                if (before == 0) s.warpCount[warp][d] = prev + __popc(peers);
+                __syncwarp();
+                pos[j] = (uint16_t)(prev + before);
+            }
         }
+        else
+        {
+#pragma unroll
+            for (int j = 0; j < KPT; j++)
+            {
+                const uint32_t d = digit_of(key[j], shift, mask);
+                atomicOr(&s.matchMask[warp][d], 1u << lane);
+                __syncwarp();
+                const uint32_t peers = s.matchMask[warp][d];
+                const uint32_t before = __popc(peers & lanemask_lt());
+                const uint32_t prev = s.warpCount[warp][d];
+                __syncwarp();
+                if (before == 0)
+                {
+                    s.warpCount[warp][d] = prev + __popc(peers);
+                    s.matchMask[warp][d] = 0u;  // ready for the next row
+                }
+                __syncwarp();
+                pos[j] = (uint16_t)(prev + before);
+            }
+        }
+        TLREC(6);
         if (wantNext)
         {
-            // next pass's digit histogram, while the keys are in registers (shared-memory atomics)
+            // next pass's digit histogram, while the keys are in registers (shared-memory REDs: 0.6-0.8 us per tile;
+            // aggregating them per warp first costs more than it saves)
 #pragma unroll
             for (int j = 0; j < KPT; j++)
             {
@@ -218,6 +292,7 @@ k_sort_onesweep(const unsigned long long* __restrict__ keysIn, const uint32_t* _
             }
         }
         __syncthreads();
+        TLREC(2);
 
         // ---- per-digit totals (thread d), publish, look back, local/global bases
         {
@@ -231,7 +306,7 @@ k_sort_onesweep(const unsigned long long* __restrict__ keysIn, const uint32_t* _
             }
             const uint32_t cnt = run;
             unsigned long long* myStatus = status + (size_t)tile * kRadixSize + tid;
-            st_relaxed_u64(myStatus, st_pack(tile == 0 ? kStPrefix : kStAggregate, gen, cnt));
+            if (digitUsed) st_relaxed_u64(myStatus, st_pack(tile == 0 ? kStPrefix : kStAggregate, gen, cnt));
 
             uint32_t incl = cnt;
 #pragma unroll
@@ -249,7 +324,7 @@ k_sort_onesweep(const unsigned long long* __restrict__ keysIn, const uint32_t* _
             const uint32_t excl = base + incl - cnt;
 
             uint32_t prior = 0;
-            if (tile > 0)
+            if (tile > 0 && digitUsed)
             {
                 // windowed look-back: kLookWindow predecessors are polled with independent loads in flight, so
                 // the walk costs one L2 round trip per window instead of one per tile
@@ -284,6 +359,7 @@ k_sort_onesweep(const unsigned long long* __restrict__ keysIn, const uint32_t* _
             s.globalBase[tid] = digitStart + prior - excl;
         }
         __syncthreads();
+        TLREC(3);
 
         // ---- reorder the tile in shared memory
 #pragma unroll
@@ -303,6 +379,7 @@ k_sort_onesweep(const unsigned long long* __restrict__ keysIn, const uint32_t* _
             s.vals[pos[j]] = val[j];
         }
         __syncthreads();
+        TLREC(4);
 
         // ---- coalesced scatter: slot i of digit d goes to globalBase[d] + i
 #pragma unroll 4
@@ -318,6 +395,7 @@ k_sort_onesweep(const unsigned long long* __restrict__ keysIn, const uint32_t* _
             }
         }
         __syncthreads();  // shared tile fully consumed before the next bulk copy lands
+        TLREC(5);
     }
     if (wantNext)
     {
@@ -351,6 +429,16 @@ static cudaError_t launch_passes_t(unsigned long long* keysA, uint32_t* valsA, u
     const uint32_t capTiles = (uint32_t)((capacity + Smem::kTile - 1) / Smem::kTile);
     const uint32_t ctasPerSM = KPT == 16 ? 3u : 5u;
     const uint32_t grid = max(1u, min((uint32_t)numSMs * ctasPerSM, capTiles));
+    unsigned long long* dTl = nullptr;
+    size_t tlWords = 0;
+#ifdef SPL_SORT_TIMELINE
+    static unsigned long long* dTlStatic = nullptr;
+    const char* tlPath = getenv("SPL_SORT_TIMELINE");
+    tlWords = (size_t)maxTiles * 8;
+    if (tlPath && !dTlStatic) cudaMalloc(&dTlStatic, kMaxSortPasses * tlWords * 8);
+    if (tlPath) cudaMemsetAsync(dTlStatic, 0, kMaxSortPasses * tlWords * 8, stream);
+    dTl = tlPath ? dTlStatic : nullptr;
+#endif
     for (int p = 0; p < passes; p++)
     {
         const unsigned long long* kin = (p & 1) ? keysB : keysA;
@@ -363,8 +451,22 @@ static cudaError_t launch_passes_t(unsigned long long* keysA, uint32_t* valsA, u
         k_sort_onesweep<KPT><<<grid, kSortThreads, sizeof(Smem), stream>>>(
             kin, vin, kout, vout, nDevice, shift, digit_mask(shift, endBit), nshift, last ? 0u : digit_mask(nshift, endBit),
             ws.histograms + (ws.passOffset + p) * kRadixSize, last ? nullptr : ws.histograms + (ws.passOffset + p + 1) * kRadixSize,
-            ws.status + (size_t)(ws.passOffset + p) * maxTiles * kRadixSize, ws.tickets + ws.passOffset + p, ws.generation);
+            ws.status + (size_t)(ws.passOffset + p) * maxTiles * kRadixSize, ws.tickets + ws.passOffset + p, ws.generation, dTl ? dTl + p * tlWords : nullptr);
     }
+#ifdef SPL_SORT_TIMELINE
+    if (tlPath)
+    {
+        cudaStreamSynchronize(stream);
+        uint32_t nHost = 0;
+        cudaMemcpy(&nHost, nDevice, 4, cudaMemcpyDeviceToHost);
+        const uint32_t tiles = (nHost + Smem::kTile - 1) / Smem::kTile;
+        std::vector<unsigned long long> h((size_t)passes * tiles * 8);
+        for (int p = 0; p < passes; p++) cudaMemcpy(h.data() + (size_t)p * tiles * 8, dTl + p * tlWords, (size_t)tiles * 64, cudaMemcpyDeviceToHost);
+        char name[512];
+        snprintf(name, sizeof name, "%s.b%d", tlPath, beginBit);
+        if (FILE* f = fopen(name, "wb")) { uint32_t hdr[4] = {(uint32_t)passes, tiles, nHost, (uint32_t)grid}; fwrite(hdr, 4, 4, f); fwrite(h.data(), 8, h.size(), f); fclose(f); }
+    }
+#endif
     return cudaGetLastError();
 }
 
