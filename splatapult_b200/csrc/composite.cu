@@ -74,7 +74,7 @@ struct CompSmem
 template <bool HALF>
 __global__ void __launch_bounds__(kCompThreads, 6)
 k_composite(const uint2* __restrict__ ranges, const uint32_t* __restrict__ vals, int idStride, const ProjRecord* __restrict__ rec,
-            void* __restrict__ fb, int width, int height, int tilesX, float earlyOutT, int cullMode)
+            void* __restrict__ fb, int width, int height, int tilesX, float earlyOutT, int cullMode, uint32_t beginXor)
 {
     __shared__ CompSmem s;
 
@@ -88,7 +88,8 @@ k_composite(const uint2* __restrict__ ranges, const uint32_t* __restrict__ vals,
     const float fx = (float)x + 0.5f, fy = (float)y + 0.5f;  // gl_FragCoord.xy
     const float tileX0 = (float)(tileX * kTileSize), tileY0 = (float)(tileY * kTileSize);
 
-    const uint2 range = ranges[tile];
+    uint2 range = ranges[tile];
+    range.x ^= beginXor;  // ranges written by the last sort pass store ~begin (kernels.h: SortWorkspace::tileRanges)
     // T == 0 marks a finished pixel: every later contribution is multiplied by it
     float T = inside ? 1.0f : 0.0f, cr = 0.0f, cg = 0.0f, cb = 0.0f;
 
@@ -256,14 +257,14 @@ k_composite(const uint2* __restrict__ ranges, const uint32_t* __restrict__ vals,
 }
 
 cudaError_t launch_composite(const uint2* ranges, const uint32_t* sortedVals, int idStrideWords, const ProjRecord* rec, void* framebuffer,
-                             int fbFormat, int width, int height, int tilesX, int tilesY, float earlyOutT, int cullMode, cudaStream_t stream)
+                             int fbFormat, int width, int height, int tilesX, int tilesY, float earlyOutT, int cullMode, uint32_t rangeBeginXor, cudaStream_t stream)
 {
     const int tiles = tilesX * tilesY;
     if (tiles <= 0) return cudaSuccess;
     if (fbFormat == 1)
-        k_composite<true><<<tiles, kCompThreads, 0, stream>>>(ranges, sortedVals, idStrideWords, rec, framebuffer, width, height, tilesX, earlyOutT, cullMode);
+        k_composite<true><<<tiles, kCompThreads, 0, stream>>>(ranges, sortedVals, idStrideWords, rec, framebuffer, width, height, tilesX, earlyOutT, cullMode, rangeBeginXor);
     else
-        k_composite<false><<<tiles, kCompThreads, 0, stream>>>(ranges, sortedVals, idStrideWords, rec, framebuffer, width, height, tilesX, earlyOutT, cullMode);
+        k_composite<false><<<tiles, kCompThreads, 0, stream>>>(ranges, sortedVals, idStrideWords, rec, framebuffer, width, height, tilesX, earlyOutT, cullMode, rangeBeginXor);
     return cudaGetLastError();
 }
 

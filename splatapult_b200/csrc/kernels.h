@@ -54,7 +54,13 @@ struct SortWorkspace
     int keysPerThread;            // 16 (4096-key tiles, 3 CTAs/SM) or 8 (2048-key tiles, 5 CTAs/SM)
     int passOffset;               // first histogram row / ticket / status region this sort uses (0..kMaxSortPasses-1):
                                   // lets two sorts of one frame (depth digits on N, tile digits on D) share the workspace
+    // optional: the LAST pass also writes each tile's range in the sorted output (tile = key >> 32), fusing the
+    // boundary-detection kernel into the scatter.  Encoding: ranges[t] = {~begin, end}, zero-initialised by the caller
+    // (so an untouched tile reads as begin = 0xFFFFFFFF, end = 0: empty); updated with atomicMax.
+    uint2* tileRanges = nullptr;
+    uint32_t numRangeTiles = 0;
 };
+constexpr uint32_t kFusedRangeBeginXor = 0xFFFFFFFFu;  // begin = ranges[t].x ^ this
 size_t sort_status_bytes(uint64_t capacity, int passes);
 // keys/vals ping-pong between (A) and (B); passes = ceil((endBit-beginBit)/8); the sorted result is in A when
 // `passes` is even, else in B.
@@ -74,6 +80,6 @@ cudaError_t launch_tile_ranges(const unsigned long long* sortedKeys, const uint3
 // ids: gaussian id of list entry k is ids[k * idStrideWords] (1: u32 payload array of the LSD sort, 2: low word of the
 // binned sort's u64 (depthKey << 32 | id) pairs)
 cudaError_t launch_composite(const uint2* ranges, const uint32_t* ids, int idStrideWords, const ProjRecord* rec, void* framebuffer, int fbFormat,
-                             int width, int height, int tilesX, int tilesY, float earlyOutT, int cullMode, cudaStream_t stream);
+                             int width, int height, int tilesX, int tilesY, float earlyOutT, int cullMode, uint32_t rangeBeginXor, cudaStream_t stream);
 
 }  // namespace splat

@@ -150,7 +150,7 @@ __global__ void __launch_bounds__(kSortThreads, KPT == 16 ? 3 : 5)
 k_sort_onesweep(const unsigned long long* __restrict__ keysIn, const uint32_t* __restrict__ valsIn, unsigned long long* __restrict__ keysOut,
                 uint32_t* __restrict__ valsOut, const uint32_t* __restrict__ nDevice, int shift, uint32_t mask, int nextShift, uint32_t nextMask,
                 const uint32_t* __restrict__ histogram, uint32_t* __restrict__ histogramNext, unsigned long long* __restrict__ status,
-                uint32_t* __restrict__ ticket, uint32_t gen, unsigned long long* tl)
+                uint32_t* __restrict__ ticket, uint32_t gen, unsigned long long* tl, uint2* __restrict__ tileRanges, uint32_t numRangeTiles)
 {
     using Smem = SortSmem<KPT>;
     constexpr int kTile = Smem::kTile;
@@ -392,6 +392,20 @@ k_sort_onesweep(const unsigned long long* __restrict__ keysIn, const uint32_t* _
                 const uint32_t g = s.globalBase[digit_of(kk, shift, mask)] + i;
                 keysOut[g] = kk;
                 valsOut[g] = s.vals[i];
+                if (tileRanges)
+                {
+                    // last pass: neighbouring slots with the same high word (tile id) are neighbours in the output too,
+                    // so only the first / last slot of each tile-id group in this CTA's tile can be a range end point
+                    const uint32_t t = (uint32_t)(kk >> 32);
+                    const uint32_t* hiWords = reinterpret_cast<const uint32_t*>(s.keys) + 1;
+                    const uint32_t tp = i > 0 ? hiWords[2 * (i - 1)] : ~t;
+                    const uint32_t tn = i + 1 < nValid ? hiWords[2 * (i + 1)] : ~t;
+                    if (t < numRangeTiles)
+                    {
+                        if (tp != t) atomicMax(&tileRanges[t].x, ~g);
+                        if (tn != t) atomicMax(&tileRanges[t].y, g + 1u);
+                    }
+                }
             }
         }
         __syncthreads();  // shared tile fully consumed before the next bulk copy lands
@@ -451,7 +465,8 @@ static cudaError_t launch_passes_t(unsigned long long* keysA, uint32_t* valsA, u
         k_sort_onesweep<KPT><<<grid, kSortThreads, sizeof(Smem), stream>>>(
             kin, vin, kout, vout, nDevice, shift, digit_mask(shift, endBit), nshift, last ? 0u : digit_mask(nshift, endBit),
             ws.histograms + (ws.passOffset + p) * kRadixSize, last ? nullptr : ws.histograms + (ws.passOffset + p + 1) * kRadixSize,
-            ws.status + (size_t)(ws.passOffset + p) * maxTiles * kRadixSize, ws.tickets + ws.passOffset + p, ws.generation, dTl ? dTl + p * tlWords : nullptr);
+            ws.status + (size_t)(ws.passOffset + p) * maxTiles * kRadixSize, ws.tickets + ws.passOffset + p, ws.generation, dTl ? dTl + p * tlWords : nullptr,
+            last && shift >= 32 ? ws.tileRanges : nullptr, ws.numRangeTiles);  // the digit must be part of the tile id
     }
 #ifdef SPL_SORT_TIMELINE
     if (tlPath)

@@ -82,6 +82,7 @@ struct RendererImpl
     float lastArgs[16 + 16 + 4 + 2] = {};
     int sortPasses = 0, sortBits = 0;
     int frameSortMode = SPL_SORT_LSD;  // sort path the last Sort() used
+    bool rangesFused = false;          // dRanges holds {~begin, end} written by the last sort pass (kernels.h)
     uint32_t launches = 0;
     cudaEvent_t ev[7] = {};
     bool evCreated = false;
@@ -122,7 +123,7 @@ struct RendererImpl
             copyStream = nullptr;
         }
         freeFrameBuffers();
-        cudaFree(dPlanes); cudaFree(dRec); cudaFree(dControl); cudaFree(dRanges); cudaFree(dFbs[0]); cudaFree(dFbs[1]); cudaFree(dTileCtl); cudaFree(dSide);
+        cudaFree(dPlanes); cudaFree(dRec); cudaFree(dControl); cudaFree(dFbs[0]); cudaFree(dFbs[1]); cudaFree(dTileCtl); cudaFree(dSide);  // dRanges lives in dControl
         dPlanes = nullptr; dRec = nullptr; dControl = nullptr; dRanges = nullptr; dFb = dFbs[0] = dFbs[1] = nullptr; dTileCtl = nullptr; dSide = nullptr;
         if (evCreated)
             for (auto& e : ev) cudaEventDestroy(e);
@@ -168,6 +169,25 @@ struct RendererImpl
         return ok();
     }
 
+    // control block: counters | digit histograms | projection scan state | tile ranges -- everything one memset per
+    // frame has to clear.  (Re)allocated when the cloud or the tile count changes; the caller has synchronised.
+    int allocControl(uint32_t tiles)
+    {
+        cudaFree(dControl);
+        dControl = nullptr;
+        const size_t scanBytes = (size_t)std::max<uint32_t>(project_num_blocks(n), 1) * sizeof(unsigned long long);
+        const size_t histBytes = kMaxSortPasses * kRadixSize * sizeof(uint32_t);
+        controlBytes = 256 + histBytes + scanBytes + (size_t)tiles * sizeof(uint2);
+        CU_TRY(cudaMalloc(&dControl, controlBytes));
+        uint8_t* base = static_cast<uint8_t*>(dControl);
+        dCtr = reinterpret_cast<FrameCounters*>(base);
+        dHist = reinterpret_cast<uint32_t*>(base + 256);
+        dScan = reinterpret_cast<unsigned long long*>(base + 256 + histBytes);
+        dRanges = reinterpret_cast<uint2*>(base + 256 + histBytes + scanBytes);
+        CU_TRY(cudaMemsetAsync(dControl, 0, controlBytes, stream));
+        return 0;
+    }
+
     int initFromDevice(const void* dAos, size_t count, size_t stride, bool fullSH, bool srgbIn)
     {
         if (int rc = begin()) return rc;
@@ -182,18 +202,11 @@ struct RendererImpl
         // drop any previous cloud
         CU_TRY(cudaStreamSynchronize(stream));
         cudaFree(dPlanes); cudaFree(dRec); cudaFree(dControl); cudaFree(dSide);
-        dPlanes = nullptr; dRec = nullptr; dControl = nullptr; dSide = nullptr;
+        dPlanes = nullptr; dRec = nullptr; dControl = nullptr; dRanges = nullptr; dSide = nullptr;
 
         n = (uint32_t)count;
         srgb = srgbIn;
-        // control block: counters | histograms | projection scan state
-        const size_t scanBytes = (size_t)std::max<uint32_t>(project_num_blocks(n), 1) * sizeof(unsigned long long);
-        controlBytes = 256 + kMaxSortPasses * kRadixSize * sizeof(uint32_t) + scanBytes;
-        CU_TRY(cudaMalloc(&dControl, controlBytes));
-        dCtr = reinterpret_cast<FrameCounters*>(dControl);
-        dHist = reinterpret_cast<uint32_t*>(static_cast<uint8_t*>(dControl) + 256);
-        dScan = reinterpret_cast<unsigned long long*>(static_cast<uint8_t*>(dControl) + 256 + kMaxSortPasses * kRadixSize * sizeof(uint32_t));
-        CU_TRY(cudaMemsetAsync(dControl, 0, controlBytes, stream));
+        if (int rc = allocControl(rangesTiles)) return rc;
 
         int shMode = 0;
         CU_TRY(detect_sh_mode(dAos, n, (uint32_t)stride, fullSH, reinterpret_cast<unsigned int*>(dControl), stream, &shMode));
@@ -257,11 +270,9 @@ struct RendererImpl
         if (numTiles > rangesTiles)
         {
             CU_TRY(cudaStreamSynchronize(stream));
-            cudaFree(dRanges);
             cudaFree(dTileCtl);
-            dRanges = nullptr;
             dTileCtl = nullptr;
-            CU_TRY(cudaMalloc(&dRanges, (size_t)numTiles * sizeof(uint2)));
+            if (int rc = allocControl(numTiles)) return rc;
             CU_TRY(cudaMalloc(&dTileCtl, (size_t)numTiles * 3 * sizeof(uint32_t)));
             rangesTiles = numTiles;
         }
@@ -277,6 +288,7 @@ struct RendererImpl
         }
         launches = 0;
         frameSortMode = sortMode;
+        rangesFused = false;
         if (profile) CU_TRY(cudaEventRecord(ev[0], stream));
         CU_TRY(cudaMemsetAsync(dControl, 0, controlBytes, stream));
         if (frameSortMode == SPL_SORT_BINNED)
@@ -305,6 +317,8 @@ struct RendererImpl
                 CU_TRY(cudaMemsetAsync(dStatus, 0, sort_status_bytes(capacity, kMaxSortPasses), stream));
                 ++sortGeneration;
             }
+            // with more than one tile the last pass sorts on a tile-id digit and writes the tile ranges itself
+            rangesFused = numTiles > 1;
             if (frameSortMode == SPL_SORT_LSD_FLAT)
             {
                 // every digit pass runs on the D tile instances (emitted in gaussian order by the projection kernel,
@@ -313,7 +327,7 @@ struct RendererImpl
                 launches += n ? 1 : 0;
                 if (profile) CU_TRY(cudaEventRecord(ev[1], stream));
                 if (profile) CU_TRY(cudaEventRecord(ev[6], stream));
-                SortWorkspace ws{dHist, dStatus, dCtr->sortTickets, capacity, sortGeneration, sortKpt, 0};
+                SortWorkspace ws{dHist, dStatus, dCtr->sortTickets, capacity, sortGeneration, sortKpt, 0, rangesFused ? dRanges : nullptr, numTiles};
                 CU_TRY(launch_sort_passes(dKeysA, dValsA, dKeysB, dValsB, &dCtr->usedInstances, capacity, 0, sortBits, ws, numSMs, stream));
                 launches += sortPasses;
                 dSortedKeys = (sortPasses & 1) ? dKeysB : dKeysA;
@@ -338,15 +352,18 @@ struct RendererImpl
                 dSortedVals = dValsB;
                 if (tilePasses > 0)
                 {
-                    SortWorkspace wsTile{dHist, dStatus, dCtr->sortTickets, capacity, sortGeneration, sortKpt, 4};
+                    SortWorkspace wsTile{dHist, dStatus, dCtr->sortTickets, capacity, sortGeneration, sortKpt, 4, rangesFused ? dRanges : nullptr, numTiles};
                     CU_TRY(launch_sort_passes(dKeysB, dValsB, dKeysA, dValsA, &dCtr->usedInstances, capacity, kDepthBits, sortBits, wsTile, numSMs, stream));
                     launches += tilePasses;
                     if (tilePasses & 1) { dSortedKeys = dKeysA; dSortedVals = dValsA; }
                 }
             }
             if (profile) CU_TRY(cudaEventRecord(ev[2], stream));
-            CU_TRY(launch_tile_ranges(dSortedKeys, &dCtr->usedInstances, capacity, dRanges, numTiles, numSMs, stream));
-            launches += 1;
+            if (!rangesFused)
+            {
+                CU_TRY(launch_tile_ranges(dSortedKeys, &dCtr->usedInstances, capacity, dRanges, numTiles, numSMs, stream));
+                launches += 1;
+            }
             if (profile) CU_TRY(cudaEventRecord(ev[3], stream));
         }
         haveSort = true;
@@ -401,7 +418,8 @@ struct RendererImpl
         fbW = fc.width; fbH = fc.height;
         if (profile) CU_TRY(cudaEventRecord(ev[4], stream));
         const bool binned = frameSortMode == SPL_SORT_BINNED;
-        CU_TRY(launch_composite(dRanges, binned ? reinterpret_cast<const uint32_t*>(dKeysA) : sortedVals(), binned ? 2 : 1, dRec, dFb, fbFormat, fc.width, fc.height, fc.tilesX, fc.tilesY, (float)earlyOutT, subblockCull, stream));
+        CU_TRY(launch_composite(dRanges, binned ? reinterpret_cast<const uint32_t*>(dKeysA) : sortedVals(), binned ? 2 : 1, dRec, dFb, fbFormat, fc.width, fc.height, fc.tilesX, fc.tilesY, (float)earlyOutT, subblockCull,
+                                rangesFused ? kFusedRangeBeginXor : 0u, stream));
         launches += 1;
         if (profile) CU_TRY(cudaEventRecord(ev[5], stream));
         CU_TRY(cudaEventRecord(evRendered[target], stream));
@@ -547,6 +565,16 @@ struct RendererImpl
         if (bytes < have) return fail(SPL_ERR_ARG, "tap buffer too small");
         if (have) CU_TRY(cudaMemcpyAsync(host, src, have, cudaMemcpyDeviceToHost, stream));
         CU_TRY(cudaStreamSynchronize(stream));
+        if (what == SPL_TAP_TILE_RANGES && rangesFused)
+        {
+            // decode {~begin, end}; a tile the sort never touched reads {0, 0}
+            uint2* r = static_cast<uint2*>(host);
+            for (size_t t = 0; t < have / sizeof(uint2); t++)
+            {
+                if (r[t].y == 0) r[t].x = 0;
+                else r[t].x ^= kFusedRangeBeginXor;
+            }
+        }
         return ok();
     }
 };
