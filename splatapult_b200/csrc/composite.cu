@@ -65,10 +65,10 @@ cudaError_t launch_tile_ranges(const unsigned long long* sortedKeys, const uint3
 // ---------------------------------------------------------------------------------------------------
 struct CompSmem
 {
-    float4 a[2][kCompChunk];    // cx, cy, A, B     with  w = 2^(A dx^2 + B dx dy + C dy^2 + L),  L = log2(alpha)
-    float4 b[2][kCompChunk];    // C, L, r, g
+    float4 a[2][kCompChunk];    // c0, c1, c2, hA   with  log2 w = c0 + c1 u + c2 v + hA u^2 + hB uv + hC v^2  (stage())
+    float4 b[2][kCompChunk];    // hB, hC, r, g
     float4 c[2][kCompChunk];    // b, -, -, -       (same index stride as a/b: one address computation per entry)
-    uint32_t mask[2][kCompChunk];  // bit (row*2+col) set: the footprint box touches that 8x4 sub-block
+    uint32_t mask[2][kCompChunk];  // bit (row*2+col) set: the splat's ellipse reaches that 8x4 sub-block
 };
 
 template <bool HALF>
@@ -85,8 +85,11 @@ k_composite(const uint2* __restrict__ ranges, const uint32_t* __restrict__ vals,
     const int x = tileX * kTileSize + subCol * kSubW + (lane & (kSubW - 1));
     const int y = tileY * kTileSize + subRow * kSubH + (lane / kSubW);
     const bool inside = x < width && y < height;
-    const float fx = (float)x + 0.5f, fy = (float)y + 0.5f;  // gl_FragCoord.xy
     const float tileX0 = (float)(tileX * kTileSize), tileY0 = (float)(tileY * kTileSize);
+    const float tileCx = tileX0 + 0.5f * kTileSize, tileCy = tileY0 + 0.5f * kTileSize;
+    // gl_FragCoord.xy = (x + 0.5, y + 0.5), kept relative to the tile centre
+    const float pu = ((float)x + 0.5f) - tileCx, pv = ((float)y + 0.5f) - tileCy;
+    const float puu = pu * pu, puv = pu * pv, pvv = pv * pv;
 
     uint2 range = ranges[tile];
     range.x ^= beginXor;  // ranges written by the last sort pass store ~begin (kernels.h: SortWorkspace::tileRanges)
@@ -117,10 +120,19 @@ k_composite(const uint2* __restrict__ ranges, const uint32_t* __restrict__ vals,
             s.mask[buf][sidx] = 0u;
             return;
         }
+        // log2 w as a polynomial in the pixel's offset (u, v) from the TILE centre: with d0 = tile centre - splat centre,
+        //   log2 w = hA (dx0+u)^2 + hB (dx0+u)(dy0+v) + hC (dy0+v)^2 + L = c0 + c1 u + c2 v + hA u^2 + hB uv + hC v^2
+        // every lane keeps u, v, u^2, uv, v^2 (|u|,|v| <= 7.5, exact in float), so an entry costs 5 FFMA instead of
+        // 2 FADD + 2 FMUL + 3 FFMA; the rounding error is that of the direct form (same term magnitudes).
         const float kLog2e = 1.4426950408889634f;
         const float h = -0.5f * kLog2e;
-        s.a[buf][sidx] = make_float4(q0.x, q0.y, h * q0.z, h * (q0.w + q1.x));
-        s.b[buf][sidx] = make_float4(h * q1.y, log2f(q2.y), q1.z, q1.w);
+        const float hA = h * q0.z, hB = h * (q0.w + q1.x), hC = h * q1.y;
+        const float dx0 = tileCx - q0.x, dy0 = tileCy - q0.y;
+        const float c0 = fmaf(dx0, fmaf(hA, dx0, hB * dy0), fmaf(hC * dy0, dy0, log2f(q2.y)));
+        const float c1 = fmaf(2.0f * hA, dx0, hB * dy0);
+        const float c2 = fmaf(2.0f * hC, dy0, hB * dx0);
+        s.a[buf][sidx] = make_float4(c0, c1, c2, hA);
+        s.b[buf][sidx] = make_float4(hB, hC, q1.z, q1.w);
         s.c[buf][sidx] = make_float4(q2.x, 0.0f, 0.0f, 0.0f);
         // Sub-block mask: which 8x4 pixel blocks can hold a pixel with alpha exp(-Q/2) > 1/256, i.e. a pixel centre
         // inside the ellipse Q(d) = A dx^2 + 2B dx dy + C dy^2 < r2, r2 = 2 ln(256 alpha) (inflated so rounding in
@@ -222,8 +234,7 @@ k_composite(const uint2* __restrict__ ranges, const uint32_t* __restrict__ vals,
                                  : "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w)
                                  : "r"(addr), "n"(sizeof(CompSmem::a)));
                     asm volatile("ld.shared.f32 %0, [%1+%2];" : "=f"(blue) : "r"(addr), "n"(sizeof(CompSmem::a) + sizeof(CompSmem::b)));
-                    const float dx = fx - a.x, dy = fy - a.y;
-                    const float pw = fmaf(dx, fmaf(a.z, dx, a.w * dy), fmaf(b.x * dy, dy, b.y));
+                    const float pw = fmaf(b.y, pvv, fmaf(b.x, puv, fmaf(a.w, puu, fmaf(a.z, pv, fmaf(a.y, pu, a.x)))));
                     const float w = ex2_approx(pw);
                     const float tw = (w > (1.0f / 256.0f)) ? T * w : 0.0f;  // discard iff w <= 1/256 (splat_frag.glsl:38)
                     cr = fmaf(tw, b.z, cr);
