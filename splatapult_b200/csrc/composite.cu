@@ -200,6 +200,7 @@ k_composite(const uint2* __restrict__ ranges, const uint32_t* __restrict__ vals,
         s.mask[buf][sidx] = m;
     };
 
+    const uint32_t warpBit = 1u << warp;
     uint32_t hi = range.y;
     if (hi > range.x) fetch(hi);
     int buf = 0;
@@ -214,14 +215,18 @@ k_composite(const uint2* __restrict__ ranges, const uint32_t* __restrict__ vals,
 
         if (__any_sync(0xffffffffu, T != 0.0f))
         {
-            for (uint32_t base = 0; base < cnt; base += 32)
+            // 32-bit shared addresses, advanced per group of 32 entries (keeps the walk out of 64-bit address math)
+            uint32_t maskAddr = (uint32_t)__cvta_generic_to_shared(&s.mask[buf][lane]);
+            uint32_t groupAddr = (uint32_t)__cvta_generic_to_shared(&s.a[buf][0]);
+            const uint32_t maskEnd = maskAddr + cnt * 4u;
+            for (; maskAddr < maskEnd; maskAddr += 32 * 4, groupAddr += 32 * 16)
             {
-                const uint32_t m = s.mask[buf][base + lane];  // slots past the list's end hold 0
-                uint32_t hits = __ballot_sync(0xffffffffu, (m >> warp) & 1u);
-                const uint32_t groupAddr = (uint32_t)__cvta_generic_to_shared(&s.a[buf][base]);
+                uint32_t m;  // slots past the list's end hold 0
+                asm volatile("ld.shared.u32 %0, [%1];" : "=r"(m) : "r"(maskAddr));
+                uint32_t hits = __ballot_sync(0xffffffffu, (m & warpBit) != 0u);
                 while (hits)
                 {
-                    // 23-instruction body: FLO, BMSK, LOP3, IMAD for the walk; 3 LDS; 15 FP32/MUFU; BRA
+                    // 21-instruction body: FLO, BMSK, LOP3, LEA for the walk; 3 LDS; 13 FP32/MUFU; BRA
                     uint32_t top, below;
                     asm("bfind.u32 %0, %1;" : "=r"(top) : "r"(hits));                       // index of the highest set bit
                     asm("bmsk.clamp.b32 %0, %1, %2;" : "=r"(below) : "r"(0), "r"(top));   // bits [0, top)
