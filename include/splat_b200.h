@@ -108,6 +108,11 @@ SPL_API int spl_renderer_framebuffer(spl_renderer*, void** device_ptr, int* widt
 SPL_API int spl_renderer_read_framebuffer_async(spl_renderer*, void* host, size_t bytes);
 /* ... or copy and wait; re-runs the frame once with a larger capacity if it overflowed */
 SPL_API int spl_renderer_read_framebuffer(spl_renderer*, void* host, size_t bytes);
+/* the PRESENTED frame: 8-bit RGBA, 4 bytes per pixel, row 0 = bottom -- the reference's RenderDesktop blit of the float
+ * target into the window (src/app.cpp:1076-1082, shader/desktop_frag.glsl:32-37): clamp to [0,1], x255, round.
+ * Converted on the device; same streaming rules as the float reads above. */
+SPL_API int spl_renderer_read_rgba8_async(spl_renderer*, void* host, size_t bytes);
+SPL_API int spl_renderer_read_rgba8(spl_renderer*, void* host, size_t bytes);
 /* device-side join: the render stream waits for every framebuffer copy still in flight (no host block) */
 SPL_API int spl_renderer_fence_copies(spl_renderer*);
 /* host-side wait: returns when at most keep_in_flight (0 or 1) async framebuffer copies are still pending; with 1,

@@ -45,6 +45,10 @@ public:
     // copies run on an internal copy stream and overlap the next frame (two render targets alternate)
     bool ReadFramebufferAsync(void* host, size_t bytes);
     bool ReadFramebuffer(void* host, size_t bytes);  // waits; transparently re-renders once on capacity overflow
+    // the PRESENTED frame, 8-bit RGBA (4 bytes / pixel, row 0 = bottom): what the reference's RenderDesktop blit leaves in
+    // the window (src/app.cpp:1076-1082); converted on the device, so a quarter of the float target's PCIe traffic
+    bool ReadPresented8Async(void* host, size_t bytes);
+    bool ReadPresented8(void* host, size_t bytes);
     bool FenceCopies();   // make the render stream wait (device-side) for every copy still in flight
     bool WaitCopies(int keepInFlight = 0);  // host waits until at most keepInFlight (0|1) async copies are pending
     bool Synchronize();   // host waits for the render stream and the copy stream

@@ -86,6 +86,8 @@ _SIGNATURES = [
                                            C.POINTER(C.c_size_t), C.POINTER(C.c_int)]),
     ("spl_renderer_read_framebuffer_async", C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
     ("spl_renderer_read_framebuffer", C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
+    ("spl_renderer_read_rgba8_async", C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
+    ("spl_renderer_read_rgba8", C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
     ("spl_renderer_fence_copies", C.c_int, [C.c_void_p]),
     ("spl_renderer_wait_copies", C.c_int, [C.c_void_p, C.c_int]),
     ("spl_renderer_synchronize", C.c_int, [C.c_void_p]),
@@ -275,6 +277,16 @@ class SplatRenderer:
 
     def ReadFramebufferAsync(self, host_ptr: int, nbytes: int) -> None:
         _check(lib().spl_renderer_read_framebuffer_async(self._h, C.c_void_p(host_ptr), nbytes))
+
+    def ReadPresented8(self) -> np.ndarray:
+        """uint8 [H, W, 4]: the presented frame (the reference's RenderDesktop blit into an 8-bit window); row 0 = bottom."""
+        _, w, h, _, _ = self.Framebuffer()
+        raw = np.empty((h, w, 4), np.uint8)
+        _check(lib().spl_renderer_read_rgba8(self._h, raw.ctypes.data, raw.nbytes))
+        return raw
+
+    def ReadPresented8Async(self, host_ptr: int, nbytes: int) -> None:
+        _check(lib().spl_renderer_read_rgba8_async(self._h, C.c_void_p(host_ptr), nbytes))
 
     def FenceCopies(self) -> None:
         """device-side join: the render stream waits for every framebuffer copy still in flight."""

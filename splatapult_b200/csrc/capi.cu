@@ -161,6 +161,16 @@ int spl_renderer_read_framebuffer(spl_renderer* h, void* host, size_t bytes)
     if (!h || !host) return set_error(SPL_ERR_ARG, "null argument");
     return from_renderer(h, h->r.ReadFramebuffer(host, bytes));
 }
+int spl_renderer_read_rgba8_async(spl_renderer* h, void* host, size_t bytes)
+{
+    if (!h || !host) return set_error(SPL_ERR_ARG, "null argument");
+    return from_renderer(h, h->r.ReadPresented8Async(host, bytes));
+}
+int spl_renderer_read_rgba8(spl_renderer* h, void* host, size_t bytes)
+{
+    if (!h || !host) return set_error(SPL_ERR_ARG, "null argument");
+    return from_renderer(h, h->r.ReadPresented8(host, bytes));
+}
 int spl_renderer_fence_copies(spl_renderer* h)
 {
     if (!h) return set_error(SPL_ERR_ARG, "null argument");

@@ -272,6 +272,40 @@ k_composite(const uint2* __restrict__ ranges, const uint32_t* __restrict__ vals,
     }
 }
 
+// ---------------------------------------------------------------------------------------------------
+// present: float target -> RGBA8, the reference's RenderDesktop blit (src/app.cpp:1076-1082; desktop_frag.glsl:32-37
+// with color = (1,1,1,1): out = texColor) into an 8-bit window: clamp to [0,1], x255, round to nearest.  NaN -> 0.
+// ---------------------------------------------------------------------------------------------------
+template <bool HALF>
+__global__ void k_present_rgba8(const void* __restrict__ fb, uint32_t* __restrict__ out, size_t pixels)
+{
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= pixels) return;
+    float4 v;
+    if (HALF)
+    {
+        const uint2 raw = reinterpret_cast<const uint2*>(fb)[i];
+        const float2 lo = __half22float2(*reinterpret_cast<const __half2*>(&raw.x));
+        const float2 hi = __half22float2(*reinterpret_cast<const __half2*>(&raw.y));
+        v = make_float4(lo.x, lo.y, hi.x, hi.y);
+    }
+    else
+    {
+        v = reinterpret_cast<const float4*>(fb)[i];
+    }
+    auto to8 = [](float c) -> uint32_t { return (uint32_t)(fminf(fmaxf(c, 0.0f), 1.0f) * 255.0f + 0.5f); };  // fmaxf(NaN, 0) = 0
+    out[i] = to8(v.x) | (to8(v.y) << 8) | (to8(v.z) << 16) | (to8(v.w) << 24);
+}
+
+cudaError_t launch_present_rgba8(const void* framebuffer, int fbFormat, uint32_t* out, size_t pixels, cudaStream_t stream)
+{
+    if (!pixels) return cudaSuccess;
+    const unsigned blocks = (unsigned)((pixels + 255) / 256);
+    if (fbFormat == 1) k_present_rgba8<true><<<blocks, 256, 0, stream>>>(framebuffer, out, pixels);
+    else k_present_rgba8<false><<<blocks, 256, 0, stream>>>(framebuffer, out, pixels);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_composite(const uint2* ranges, const uint32_t* sortedVals, int idStrideWords, const ProjRecord* rec, void* framebuffer,
                              int fbFormat, int width, int height, int tilesX, int tilesY, float earlyOutT, int cullMode, uint32_t rangeBeginXor, cudaStream_t stream)
 {

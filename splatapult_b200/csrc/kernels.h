@@ -82,4 +82,7 @@ cudaError_t launch_tile_ranges(const unsigned long long* sortedKeys, const uint3
 cudaError_t launch_composite(const uint2* ranges, const uint32_t* ids, int idStrideWords, const ProjRecord* rec, void* framebuffer, int fbFormat,
                              int width, int height, int tilesX, int tilesY, float earlyOutT, int cullMode, uint32_t rangeBeginXor, cudaStream_t stream);
 
+// float target -> packed RGBA8 (R in the low byte), same pixel order as the target
+cudaError_t launch_present_rgba8(const void* framebuffer, int fbFormat, uint32_t* out, size_t pixels, cudaStream_t stream);
+
 }  // namespace splat

@@ -69,6 +69,8 @@ struct RendererImpl
     uint32_t rangesTiles = 0;
     void* dFb = nullptr;             // target of the last Render (= dFbs[fbCur])
     void* dFbs[2] = {nullptr, nullptr};
+    void* dPresent[2] = {nullptr, nullptr};  // RGBA8 images of the two targets (allocated on first ReadPresented8)
+    size_t presentBytes = 0;
     int fbNext = 0, fbCur = 0;
     cudaStream_t copyStream = nullptr;  // framebuffer D->H copies overlap the next frame
     cudaEvent_t evRendered[2] = {}, evCopied[2] = {};
@@ -124,6 +126,9 @@ struct RendererImpl
         }
         freeFrameBuffers();
         cudaFree(dPlanes); cudaFree(dRec); cudaFree(dControl); cudaFree(dFbs[0]); cudaFree(dFbs[1]); cudaFree(dTileCtl); cudaFree(dSide);  // dRanges lives in dControl
+        cudaFree(dPresent[0]); cudaFree(dPresent[1]);
+        dPresent[0] = dPresent[1] = nullptr;
+        presentBytes = 0;
         dPlanes = nullptr; dRec = nullptr; dControl = nullptr; dRanges = nullptr; dFb = dFbs[0] = dFbs[1] = nullptr; dTileCtl = nullptr; dSide = nullptr;
         if (evCreated)
             for (auto& e : ev) cudaEventDestroy(e);
@@ -463,11 +468,13 @@ struct RendererImpl
         return 0;
     }
 
-    int readFramebuffer(void* host, size_t bytes, bool wait)
+    // rgba8 = the presented frame: what the reference's RenderDesktop blit (src/app.cpp:1076-1082,
+    // shader/desktop_frag.glsl:32-37 with color = (1,1,1,1)) leaves in the 8-bit window: clamp to [0,1], x255, round
+    int readFramebuffer(void* host, size_t bytes, bool wait, bool rgba8 = false)
     {
         if (int rc = begin()) return rc;
         if (!haveRender) return fail(SPL_ERR_ARG, "no frame rendered yet");
-        const size_t need = (size_t)fbW * fbH * (fbFormat == SPL_FB_FP16 ? 8 : 16);
+        const size_t need = (size_t)fbW * fbH * (rgba8 ? 4 : fbFormat == SPL_FB_FP16 ? 8 : 16);
         if (bytes < need) return fail(SPL_ERR_ARG, "host buffer too small for the framebuffer");
         if (wait)
         {
@@ -486,8 +493,29 @@ struct RendererImpl
         }
         // device -> host on the copy stream, ordered after the composite of this target by an event; the next
         // Render writes the other target, so it overlaps this copy
+        const void* src = dFb;
+        if (rgba8)
+        {
+            if (presentBytes != need)
+            {
+                CU_TRY(cudaStreamSynchronize(stream));
+                CU_TRY(cudaStreamSynchronize(copyStream));
+                for (int k = 0; k < 2; k++)
+                {
+                    cudaFree(dPresent[k]);
+                    dPresent[k] = nullptr;
+                    CU_TRY(cudaMalloc(&dPresent[k], need));
+                }
+                presentBytes = need;
+            }
+            // one 8-bit image per render target: the next Render into this target already waits for evCopied[fbCur]
+            CU_TRY(launch_present_rgba8(dFb, fbFormat, static_cast<uint32_t*>(dPresent[fbCur]), (size_t)fbW * fbH, stream));
+            launches += 1;
+            CU_TRY(cudaEventRecord(evRendered[fbCur], stream));
+            src = dPresent[fbCur];
+        }
         CU_TRY(cudaStreamWaitEvent(copyStream, evRendered[fbCur], 0));
-        CU_TRY(cudaMemcpyAsync(host, dFb, need, cudaMemcpyDeviceToHost, copyStream));
+        CU_TRY(cudaMemcpyAsync(host, src, need, cudaMemcpyDeviceToHost, copyStream));
         CU_TRY(cudaEventRecord(evCopied[fbCur], copyStream));
         copyPending[fbCur] = true;
         if (wait) CU_TRY(cudaStreamSynchronize(copyStream));
@@ -644,6 +672,10 @@ bool SplatRenderer::GetFramebuffer(void** devicePtr, int* width, int* height, si
 
 bool SplatRenderer::ReadFramebufferAsync(void* host, size_t bytes) { FORWARD(impl->readFramebuffer(host, bytes, false)); }
 bool SplatRenderer::ReadFramebuffer(void* host, size_t bytes) { FORWARD(impl->readFramebuffer(host, bytes, true)); }
+
+bool SplatRenderer::ReadPresented8Async(void* host, size_t bytes) { FORWARD(impl->readFramebuffer(host, bytes, false, true)); }
+
+bool SplatRenderer::ReadPresented8(void* host, size_t bytes) { FORWARD(impl->readFramebuffer(host, bytes, true, true)); }
 
 bool SplatRenderer::Synchronize()
 {

@@ -91,3 +91,38 @@ def test_fp16_async_and_resolution_change(splat, golden_dir):
     assert fb[..., 3].min() == 1.0 and fb[..., :3].max() > 0.1
     with pytest.raises(splat.SplatError):
         r.ReadFramebufferAsync(a.ptr, 16)  # buffer too small
+
+
+@pytest.mark.parametrize("fb_format", [api.FB_FP32, api.FB_FP16])
+def test_presented_rgba8_is_the_desktop_blit(splat, golden_dir, fb_format):
+    """ReadPresented8 = the reference's RenderDesktop blit (src/app.cpp:1076-1082, desktop_frag.glsl:32-37, color = 1)
+    into an 8-bit window: clamp, x255, round -- bit-exact against the host conversion of the float target."""
+    g = np.load(os.path.join(golden_dir, "synth_2k_deg3_320x180.npz"))
+    gc = splat.GaussianCloud()
+    gc.SetRawData(g["aos"], True)
+    r = splat.SplatRenderer(fb_format=fb_format)
+    assert r.Init(gc, False, False)
+    vp = [0, 0, 320, 180]
+    r.Render(g["camera"], g["proj"], vp, NF)
+    fb = r.ReadFramebuffer()
+    want = (np.clip(fb, 0.0, 1.0) * np.float32(255.0) + np.float32(0.5)).astype(np.uint8)
+    got = r.ReadPresented8()
+    assert got.shape == (180, 320, 4) and got.dtype == np.uint8
+    np.testing.assert_array_equal(got, want)
+    assert got[..., 3].min() == 255 and got[..., :3].max() > 100
+
+    # streamed: three frames, 8-bit copies overlapping the next frame
+    cams = [g["camera"], scenes.translate(0.7, -0.3, 9.0), scenes.translate(-1.0, 0.4, 11.0)]
+    wants, pinned = [], [splat.host_alloc(320 * 180 * 4) for _ in cams]
+    for c in cams:
+        r.Render(c, g["proj"], vp, NF)
+        wants.append(r.ReadPresented8().copy())
+    for k, c in enumerate(cams):
+        r.Sort(c, g["proj"], vp, NF)
+        r.Render(c, g["proj"], vp, NF)
+        r.ReadPresented8Async(pinned[k].ptr, pinned[k].nbytes)
+    r.WaitCopies(0)
+    for k in range(3):
+        np.testing.assert_array_equal(pinned[k].array(np.uint8, (180, 320, 4)), wants[k])
+    with pytest.raises(api.SplatError):
+        r.ReadPresented8Async(pinned[0].ptr, 16)
