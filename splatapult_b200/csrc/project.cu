@@ -257,20 +257,13 @@ __device__ __forceinline__ Projected project_gaussian(const PackedCloud& cloud, 
     return out;
 }
 
-// Two uses of one kernel body (scan of tile counts + coalesced key emission):
-//   FROM_SORTED = false ("flat" LSD path): projects gaussian i itself and emits its keys in index order; the
-//       histogram it leaves for the sorter is that of the keys' LOWEST digit (weighted by the tile count);
-//   FROM_SORTED = true (default LSD path): entry j of the depth-sorted gaussian list (sortedKeys low word = depthKey,
-//       sortedVals = gaussian id, side[id] = tile rectangle) -- the projection was done by k_project_keys and the
-//       four depth-digit passes have already run on the N gaussians; keys are emitted in depth order and the
-//       histogram is that of the FIRST TILE digit (bits 32..39), one count per instance.
-template <int SH_MODE, bool FROM_SORTED>
+// "Flat" LSD path: projects gaussian i, scans the tile counts (decoupled look-back) and emits its keys in index order;
+// the histogram it leaves for the sorter is that of the keys' LOWEST digit (weighted by the tile count).
+template <int SH_MODE>
 __global__ void __launch_bounds__(kProjThreads)
 k_project(const PackedCloud cloud, const __grid_constant__ FrameConstants fc, ProjRecord* __restrict__ rec,
           unsigned long long* __restrict__ keys, uint32_t* __restrict__ vals, FrameCounters* __restrict__ ctr,
-          unsigned long long* __restrict__ scanState, uint32_t capacity, uint32_t* __restrict__ digit0Hist,
-          const unsigned long long* __restrict__ sortedKeys, const uint32_t* __restrict__ sortedVals, const uint2* __restrict__ side,
-          uint32_t nSorted)
+          unsigned long long* __restrict__ scanState, uint32_t capacity, uint32_t* __restrict__ digit0Hist)
 {
     __shared__ uint32_t sBlockId;
     __shared__ uint32_t sWarpTotal[kProjThreads / 32];
@@ -285,21 +278,6 @@ k_project(const PackedCloud cloud, const __grid_constant__ FrameConstants fc, Pr
     uint32_t i = vbid * kProjThreads + tid;  // gaussian id
     uint32_t count = 0, refKey = 0, rect = 0;
     bool visible = false;
-    if (FROM_SORTED)
-    {
-        const uint32_t j = i;
-        i = 0;
-        if (j < nSorted)
-        {
-            i = __ldg(sortedVals + j);
-            const uint2 sd = __ldg(side + i);
-            const uint32_t w = sd.y & 0xffffu, h = sd.y >> 16;
-            count = w * h;
-            rect = (sd.x & 0xffffu) | ((sd.x >> 16) << 10) | ((w ? w - 1 : 0) << 20);
-            refKey = (uint32_t)__ldg(sortedKeys + j);
-        }
-    }
-    else
     {
         const Projected pg = project_gaussian<SH_MODE>(cloud, fc, rec, i, i < cloud.n);
         count = pg.count;
@@ -372,7 +350,7 @@ k_project(const PackedCloud cloud, const __grid_constant__ FrameConstants fc, Pr
     if (!fits) atomicOr(&ctr->overflow, 1u);
     const uint32_t gOff = fits ? (uint32_t)gOff64 : 0u;
     // flat path: all cntE keys of this gaussian share their low 32 bits, one weighted update covers them
-    if (!FROM_SORTED && cntE && digit0Hist) smem_red_add(&sDigit0[refKey & (kRadixSize - 1)], cntE);
+    if (cntE && digit0Hist) smem_red_add(&sDigit0[refKey & (kRadixSize - 1)], cntE);
 
     uint32_t inclE = cntE;
 #pragma unroll
@@ -414,7 +392,6 @@ k_project(const PackedCloud cloud, const __grid_constant__ FrameConstants fc, Pr
             const uint32_t tile = (y0 + row) * tilesX + (x0 + col);
             keys[oOff + k] = ((unsigned long long)tile << 32) | oKey;
             vals[oOff + k] = oId;
-            if (FROM_SORTED && digit0Hist) smem_red_add(&sDigit0[tile & (kRadixSize - 1)], 1u);  // first tile digit
         }
     }
     if (digit0Hist)
@@ -422,6 +399,177 @@ k_project(const PackedCloud cloud, const __grid_constant__ FrameConstants fc, Pr
         __syncthreads();
         const uint32_t c = sDigit0[tid];
         if (c) atomicAdd(digit0Hist + tid, c);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// default LSD path, step 2: expand the depth-sorted gaussian list into (tile << 32 | depthKey, id) instances, in
+// depth order.  Same scan + look-back + warp-cooperative emission as k_project, but every thread carries
+// kEmitRounds entries (entry j = cta * 1024 + round * 256 + tid, so loads stay coalesced and the emission order is
+// the list order): a quarter of the CTAs means a quarter of the links in the look-back chain.  With one entry per
+// thread the walkers (32 predecessors per L2 round trip) were slower than the rate at which new CTAs start, so the
+// walks kept growing and 7 of 8 warps sat on the barrier behind warp 0 (ncu: barrier stall 21 warps per issue).
+// ---------------------------------------------------------------------------------------------------
+constexpr int kEmitRounds = 4;
+
+__global__ void __launch_bounds__(kProjThreads)
+k_emit_sorted(const unsigned long long* __restrict__ sortedKeys, const uint32_t* __restrict__ sortedVals, const uint2* __restrict__ side,
+              uint32_t nSorted, uint32_t tilesX, unsigned long long* __restrict__ keys, uint32_t* __restrict__ vals,
+              FrameCounters* __restrict__ ctr, unsigned long long* __restrict__ scanState, uint32_t capacity, uint32_t* __restrict__ tileDigitHist)
+{
+    constexpr int kWarps = kProjThreads / 32;
+    __shared__ uint32_t sBlockId;
+    __shared__ uint32_t sWarpTotal[kEmitRounds][kWarps];
+    __shared__ unsigned long long sBlockBase;
+    __shared__ uint32_t sDigit0[kRadixSize];  // histogram of the first tile digit (bits 32..39), one count per instance
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) sBlockId = atomicAdd(&ctr->projectTicket, 1u);  // dynamic id: predecessors are resident or done
+    sDigit0[tid] = 0;
+    __syncthreads();
+    const uint32_t vbid = sBlockId;
+
+    uint32_t count[kEmitRounds], rect[kEmitRounds], refKey[kEmitRounds], id[kEmitRounds], incl[kEmitRounds];
+#pragma unroll
+    for (int r = 0; r < kEmitRounds; r++)
+    {
+        const uint32_t j = (vbid * kEmitRounds + r) * kProjThreads + tid;
+        count[r] = 0; rect[r] = 0; refKey[r] = 0; id[r] = 0;
+        if (j < nSorted)
+        {
+            id[r] = __ldg(sortedVals + j);
+            const uint2 sd = __ldg(side + id[r]);
+            const uint32_t w = sd.y & 0xffffu, h = sd.y >> 16;
+            count[r] = w * h;
+            rect[r] = (sd.x & 0xffffu) | ((sd.x >> 16) << 10) | ((w ? w - 1 : 0) << 20);
+            refKey[r] = (uint32_t)__ldg(sortedKeys + j);
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < kEmitRounds; r++)
+    {
+        uint32_t v = count[r];
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1)
+        {
+            const uint32_t u = __shfl_up_sync(0xffffffffu, v, d);
+            if (lane >= d) v += u;
+        }
+        incl[r] = v;
+        if (lane == 31) sWarpTotal[r][warp] = v;
+    }
+    __syncthreads();
+    uint32_t base[kEmitRounds];  // CTA-relative offset of this warp's first instance of round r
+    uint32_t blockTotal = 0;
+#pragma unroll
+    for (int r = 0; r < kEmitRounds; r++)
+    {
+        uint32_t before = 0, total = 0;
+#pragma unroll
+        for (int w = 0; w < kWarps; w++)
+        {
+            const uint32_t t = sWarpTotal[r][w];
+            if (w < warp) before += t;
+            total += t;
+        }
+        base[r] = blockTotal + before;
+        blockTotal += total;
+    }
+
+    // ---- decoupled look-back over CTA aggregates (warp 0)
+    if (warp == 0)
+    {
+        unsigned long long excl = 0;
+        if (lane == 0) st_relaxed_u64(scanState + vbid, (vbid == 0 ? kScanPrefix : kScanAggregate) | blockTotal);
+        if (vbid > 0)
+        {
+            int b0 = (int)vbid - 1;
+            for (;;)
+            {
+                const int j = b0 - lane;
+                unsigned long long s = kScanPrefix;  // virtual predecessor of block 0: prefix 0
+                if (j >= 0)
+                {
+                    do { s = ld_relaxed_u64(scanState + j); } while ((s >> 62) == 0);
+                }
+                const bool isPrefix = (s >> 62) == 2;
+                const uint32_t pmask = __ballot_sync(0xffffffffu, isPrefix);
+                const int firstP = pmask ? (__ffs(pmask) - 1) : 32;
+                unsigned long long v = (lane <= firstP) ? (s & kScanValueMask) : 0ull;
+#pragma unroll
+                for (int d = 16; d; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+                excl += v;
+                if (pmask) break;
+                b0 -= 32;
+            }
+            if (lane == 0) st_relaxed_u64(scanState + vbid, kScanPrefix | (excl + blockTotal));
+        }
+        if (lane == 0)
+        {
+            sBlockBase = excl;
+            if (vbid == gridDim.x - 1) ctr->totalInstances = excl + blockTotal;
+        }
+    }
+    __syncthreads();
+
+    // ---- warp-cooperative, coalesced emission, one round at a time
+    const unsigned long long blockBase = sBlockBase;
+    uint32_t usedEnd = 0;
+#pragma unroll
+    for (int r = 0; r < kEmitRounds; r++)
+    {
+        const unsigned long long gOff64 = blockBase + base[r] + (incl[r] - count[r]);
+        const bool fits = gOff64 + count[r] <= (unsigned long long)capacity;
+        const uint32_t cntE = fits ? count[r] : 0u;
+        if (!fits) atomicOr(&ctr->overflow, 1u);
+        const uint32_t gOff = fits ? (uint32_t)gOff64 : 0u;
+        if (cntE) usedEnd = max(usedEnd, gOff + cntE);
+
+        uint32_t inclE = cntE;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1)
+        {
+            const uint32_t v = __shfl_up_sync(0xffffffffu, inclE, d);
+            if (lane >= d) inclE += v;
+        }
+        const uint32_t wexE = inclE - cntE;
+        const uint32_t T = __shfl_sync(0xffffffffu, inclE, 31);
+        for (uint32_t j0 = 0; j0 < T; j0 += 32)
+        {
+            const uint32_t j = j0 + lane;
+            int owner = 0;
+#pragma unroll
+            for (int s = 16; s; s >>= 1)
+            {
+                const int cand = owner + s;
+                const uint32_t v = __shfl_sync(0xffffffffu, wexE, cand);
+                if (v <= j) owner = cand;
+            }
+            const uint32_t oBase = __shfl_sync(0xffffffffu, wexE, owner);
+            const uint32_t oOff = __shfl_sync(0xffffffffu, gOff, owner);
+            const uint32_t oRect = __shfl_sync(0xffffffffu, rect[r], owner);
+            const uint32_t oKey = __shfl_sync(0xffffffffu, refKey[r], owner);
+            const uint32_t oId = __shfl_sync(0xffffffffu, id[r], owner);
+            if (j < T)
+            {
+                const uint32_t k = j - oBase;
+                const uint32_t w = (oRect >> 20) + 1, x0 = oRect & 1023u, y0 = (oRect >> 10) & 1023u;
+                const uint32_t row = k / w, col = k - row * w;
+                const uint32_t tile = (y0 + row) * tilesX + (x0 + col);
+                keys[oOff + k] = ((unsigned long long)tile << 32) | oKey;
+                vals[oOff + k] = oId;
+                if (tileDigitHist) smem_red_add(&sDigit0[tile & (kRadixSize - 1)], 1u);
+            }
+        }
+    }
+#pragma unroll
+    for (int d = 16; d; d >>= 1) usedEnd = max(usedEnd, __shfl_xor_sync(0xffffffffu, usedEnd, d));
+    if (lane == 0 && usedEnd) atomicMax(&ctr->usedInstances, usedEnd);
+    if (tileDigitHist)
+    {
+        __syncthreads();
+        const uint32_t c = sDigit0[tid];
+        if (c) atomicAdd(tileDigitHist + tid, c);
     }
 }
 
@@ -593,9 +741,9 @@ cudaError_t launch_project(const PackedCloud& cloud, const FrameConstants& fc, P
     if (blocks == 0) return cudaSuccess;
     switch (cloud.shMode)
     {
-    case 0: k_project<0, false><<<blocks, kProjThreads, 0, stream>>>(cloud, fc, rec, keys, vals, ctr, scanState, capacity, digit0Hist, nullptr, nullptr, nullptr, 0); break;
-    case 1: k_project<1, false><<<blocks, kProjThreads, 0, stream>>>(cloud, fc, rec, keys, vals, ctr, scanState, capacity, digit0Hist, nullptr, nullptr, nullptr, 0); break;
-    default: k_project<3, false><<<blocks, kProjThreads, 0, stream>>>(cloud, fc, rec, keys, vals, ctr, scanState, capacity, digit0Hist, nullptr, nullptr, nullptr, 0); break;
+    case 0: k_project<0><<<blocks, kProjThreads, 0, stream>>>(cloud, fc, rec, keys, vals, ctr, scanState, capacity, digit0Hist); break;
+    case 1: k_project<1><<<blocks, kProjThreads, 0, stream>>>(cloud, fc, rec, keys, vals, ctr, scanState, capacity, digit0Hist); break;
+    default: k_project<3><<<blocks, kProjThreads, 0, stream>>>(cloud, fc, rec, keys, vals, ctr, scanState, capacity, digit0Hist); break;
     }
     return cudaGetLastError();
 }
@@ -618,11 +766,11 @@ cudaError_t launch_emit_sorted(const unsigned long long* sortedKeys, const uint3
                                const FrameConstants& fc, unsigned long long* keys, uint32_t* vals, FrameCounters* ctr,
                                unsigned long long* scanState, uint32_t capacity, uint32_t* tileDigitHist, cudaStream_t stream)
 {
-    const uint32_t blocks = project_num_blocks(n);
+    const uint32_t perCta = kProjThreads * kEmitRounds;
+    const uint32_t blocks = (n + perCta - 1) / perCta;  // <= project_num_blocks(n): scanState is large enough
     if (blocks == 0) return cudaSuccess;
-    PackedCloud none{};
-    k_project<0, true><<<blocks, kProjThreads, 0, stream>>>(none, fc, nullptr, keys, vals, ctr, scanState, capacity, tileDigitHist, sortedKeys, sortedVals,
-                                                           side, n);
+    k_emit_sorted<<<blocks, kProjThreads, 0, stream>>>(sortedKeys, sortedVals, side, n, (uint32_t)fc.tilesX, keys, vals, ctr, scanState, capacity,
+                                                       tileDigitHist);
     return cudaGetLastError();
 }
 
