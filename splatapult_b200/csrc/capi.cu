@@ -312,7 +312,7 @@ int spl_sorter_sort(spl_sorter* s, void* d_keys_in, void* d_vals_in, void* d_key
     const uint32_t n32 = (uint32_t)n;
     SORTER_TRY(cudaMemcpyAsync(s->control, &n32, sizeof n32, cudaMemcpyHostToDevice, stream));
     uint32_t* ctl = static_cast<uint32_t*>(s->control);
-    if (((++s->generation) & 0xffffu) == 0)
+    if (((++s->generation) & splat::kSortGenerationMask) == 0)
     {
         SORTER_TRY(cudaMemsetAsync(s->status, 0, splat::sort_status_bytes(s->capacity, splat::kMaxSortPasses), stream));
         ++s->generation;

@@ -20,6 +20,9 @@ constexpr int kSortThreads = 256;    // onesweep CTA
 constexpr int kSortKeysPerThread = 16;
 constexpr int kSortTileKeys = kSortThreads * kSortKeysPerThread;  // 4096 keys = 32 KiB staged by one bulk copy
 constexpr int kSortMinTileKeys = kSortThreads * 8;                // smallest tile variant (sizes the look-back array)
+// look-back words carry a 5-bit generation instead of being cleared per sort: the owner of the status array bumps its
+// generation per sort and zeroes the array whenever (generation & mask) wraps to 0 (every 31 sorts)
+constexpr uint32_t kSortGenerationMask = 31;
 
 // look-back status word: [31:30] flag, [29:0] count
 constexpr uint32_t kFlagAggregate = 1u << 30;
@@ -137,6 +140,16 @@ __device__ __forceinline__ uint32_t ld_relaxed_u32(const uint32_t* p)
 __device__ __forceinline__ void st_relaxed_u32(uint32_t* p, uint32_t v)
 {
     asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_u32(const uint32_t* p)
+{
+    uint32_t v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_u32(uint32_t* p, uint32_t v)
+{
+    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 __device__ __forceinline__ unsigned long long ld_relaxed_u64(const unsigned long long* p)
 {

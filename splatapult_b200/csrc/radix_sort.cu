@@ -38,14 +38,21 @@ __host__ __device__ __forceinline__ uint32_t digit_mask(int shift, int endBit)
 // below this effective number of digit values (1 / sum of squared bin fractions) a pass ranks with MATCH.ANY
 constexpr int kMatchAnyMaxValues = 4;
 
-// look-back status word: [63:62] flag, [47:32] generation, [31:0] count
-constexpr unsigned long long kStAggregate = 1ull << 62;
-constexpr unsigned long long kStPrefix = 2ull << 62;
-__device__ __forceinline__ unsigned long long st_pack(unsigned long long flag, uint32_t gen, uint32_t count)
+// Look-back status.  The walk over predecessor tiles is L2-bandwidth bound (a tile reads ~150 predecessor rows of 256
+// words against 48 KB of key data), so the word every walker reads is 32 bits:
+//   lo[tile][digit] = [31:30] flag | [29] has-hi | [28:24] generation (kSortGenerationMask) | [23:0] count, low 24 bits
+//   hi[tile][digit] = count >> 24   -- written (before lo, which is then stored with release) and read (after an acquire
+//                                      re-read of lo) only for a PREFIX of 2^24 or more: one digit value with more
+//                                      than 16.7 M keys in front of the tile.  Everything else is relaxed 32-bit traffic.
+constexpr uint32_t kStAggregate = 1u << 30;
+constexpr uint32_t kStPrefix = 2u << 30;
+constexpr uint32_t kStHasHi = 1u << 29;
+constexpr uint32_t kStCountMask = (1u << 24) - 1u;
+__device__ __forceinline__ uint32_t st_pack(uint32_t flag, uint32_t gen, uint32_t count)
 {
-    return flag | ((unsigned long long)(gen & 0xffffu) << 32) | count;
+    return flag | ((gen & kSortGenerationMask) << 24) | (count & kStCountMask);
 }
-__device__ __forceinline__ bool st_valid(unsigned long long w, uint32_t gen) { return (w >> 62) != 0 && (uint32_t)((w >> 32) & 0xffffu) == (gen & 0xffffu); }
+__device__ __forceinline__ bool st_valid(uint32_t w, uint32_t gen) { return (w >> 30) != 0 && ((w >> 24) & kSortGenerationMask) == (gen & kSortGenerationMask); }
 
 // ---------------------------------------------------------------------------------------------------
 // S1 (stand-alone sorter only): histogram of the FIRST digit; TMA-staged, double-buffered
@@ -150,7 +157,8 @@ __global__ void __launch_bounds__(kSortThreads, KPT == 16 ? 3 : 5)
 k_sort_onesweep(const unsigned long long* __restrict__ keysIn, const uint32_t* __restrict__ valsIn, unsigned long long* __restrict__ keysOut,
                 uint32_t* __restrict__ valsOut, const uint32_t* __restrict__ nDevice, int shift, uint32_t mask, int nextShift, uint32_t nextMask,
                 const uint32_t* __restrict__ histogram, uint32_t* __restrict__ histogramNext, unsigned long long* __restrict__ status,
-                uint32_t* __restrict__ ticket, uint32_t gen, unsigned long long* tl, uint2* __restrict__ tileRanges, uint32_t numRangeTiles)
+                uint32_t* __restrict__ ticket, uint32_t gen, unsigned long long* tl, uint2* __restrict__ tileRanges, uint32_t numRangeTiles,
+                uint32_t statusTiles)
 {
     using Smem = SortSmem<KPT>;
     constexpr int kTile = Smem::kTile;
@@ -162,6 +170,8 @@ k_sort_onesweep(const unsigned long long* __restrict__ keysIn, const uint32_t* _
     const uint32_t n = *nDevice;
     const uint32_t numTiles = (n + kTile - 1) / kTile;
     const bool wantNext = histogramNext != nullptr;
+    uint32_t* const statusLo = reinterpret_cast<uint32_t*>(status);
+    uint32_t* const statusHi = statusLo + (size_t)statusTiles * kRadixSize;
 
     // global exclusive scan of this pass's digit histogram: thread d owns digit d
     uint32_t digitStart;
@@ -305,8 +315,19 @@ k_sort_onesweep(const unsigned long long* __restrict__ keysIn, const uint32_t* _
                 run += c;
             }
             const uint32_t cnt = run;
-            unsigned long long* myStatus = status + (size_t)tile * kRadixSize + tid;
-            if (digitUsed) st_relaxed_u64(myStatus, st_pack(tile == 0 ? kStPrefix : kStAggregate, gen, cnt));
+            uint32_t* myLo = statusLo + (size_t)tile * kRadixSize + tid;
+            uint32_t* myHi = statusHi + (size_t)tile * kRadixSize + tid;
+            if (digitUsed)
+            {
+                if (tile == 0)
+                {
+                    st_relaxed_u32(myLo, st_pack(kStPrefix, gen, cnt));  // cnt <= tile size: no high part
+                }
+                else
+                {
+                    st_relaxed_u32(myLo, st_pack(kStAggregate, gen, cnt));
+                }
+            }
 
             uint32_t incl = cnt;
 #pragma unroll
@@ -330,13 +351,13 @@ k_sort_onesweep(const unsigned long long* __restrict__ keysIn, const uint32_t* _
                 // the walk costs one L2 round trip per window instead of one per tile
                 constexpr int kLookWindow = 8;
                 int t = (int)tile - 1;
-                bool done = false;
+                bool done = false, hasHi = false;
                 while (!done)
                 {
-                    unsigned long long v[kLookWindow];
+                    uint32_t v[kLookWindow];
 #pragma unroll
                     for (int i = 0; i < kLookWindow; i++)
-                        v[i] = (t - i >= 0) ? ld_relaxed_u64(status + (size_t)(t - i) * kRadixSize + tid) : st_pack(kStPrefix, gen, 0u);
+                        v[i] = (t - i >= 0) ? ld_relaxed_u32(statusLo + (size_t)(t - i) * kRadixSize + tid) : st_pack(kStPrefix, gen, 0u);
                     int used = 0;
 #pragma unroll
                     for (int i = 0; i < kLookWindow; i++)
@@ -345,15 +366,32 @@ k_sort_onesweep(const unsigned long long* __restrict__ keysIn, const uint32_t* _
                         {
                             if (st_valid(v[i], gen))
                             {
-                                prior += (uint32_t)v[i];
+                                prior += v[i] & kStCountMask;
                                 used = i + 1;
-                                done = (v[i] >> 62) == 2;
+                                done = (v[i] >> 30) == 2;
+                                hasHi = done && (v[i] & kStHasHi) != 0u;
                             }
                         }
                     }
                     t -= used;  // re-poll from the first word that was not yet published
                 }
-                st_relaxed_u64(myStatus, st_pack(kStPrefix, gen, prior + cnt));
+                // the walk ended on the prefix word of tile t + 1; if that prefix did not fit 24 bits its publisher stored
+                // hi, then lo with release: re-read lo with acquire, then hi
+                if (hasHi)
+                {
+                    (void)ld_acquire_u32(statusLo + (size_t)(t + 1) * kRadixSize + tid);
+                    prior += ld_relaxed_u32(statusHi + (size_t)(t + 1) * kRadixSize + tid) << 24;
+                }
+                const uint32_t total = prior + cnt;
+                if (total > kStCountMask)
+                {
+                    st_relaxed_u32(myHi, total >> 24);
+                    st_release_u32(myLo, st_pack(kStPrefix | kStHasHi, gen, total));
+                }
+                else
+                {
+                    st_relaxed_u32(myLo, st_pack(kStPrefix, gen, total));
+                }
             }
             s.ctaExcl[tid] = excl;
             s.globalBase[tid] = digitStart + prior - excl;
@@ -466,7 +504,8 @@ static cudaError_t launch_passes_t(unsigned long long* keysA, uint32_t* valsA, u
             kin, vin, kout, vout, nDevice, shift, digit_mask(shift, endBit), nshift, last ? 0u : digit_mask(nshift, endBit),
             ws.histograms + (ws.passOffset + p) * kRadixSize, last ? nullptr : ws.histograms + (ws.passOffset + p + 1) * kRadixSize,
             ws.status + (size_t)(ws.passOffset + p) * maxTiles * kRadixSize, ws.tickets + ws.passOffset + p, ws.generation, dTl ? dTl + p * tlWords : nullptr,
-            last && shift >= 32 ? ws.tileRanges : nullptr, ws.numRangeTiles);  // the digit must be part of the tile id
+            last && shift >= 32 ? ws.tileRanges : nullptr, ws.numRangeTiles,  // the digit must be part of the tile id
+            (uint32_t)maxTiles);
     }
 #ifdef SPL_SORT_TIMELINE
     if (tlPath)

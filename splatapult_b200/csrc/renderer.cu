@@ -316,8 +316,8 @@ struct RendererImpl
         else
         {
             // LSD: device-wide onesweep radix sort of the packed (tile << 32 | depthKey) keys, then boundary detection.
-            // look-back words are generation-tagged instead of cleared; re-zero only when the 16-bit tag wraps
-            if (((++sortGeneration) & 0xffffu) == 0)
+            // look-back words are generation-tagged instead of cleared; re-zero only when the 6-bit tag wraps
+            if (((++sortGeneration) & kSortGenerationMask) == 0)
             {
                 CU_TRY(cudaMemsetAsync(dStatus, 0, sort_status_bytes(capacity, kMaxSortPasses), stream));
                 ++sortGeneration;

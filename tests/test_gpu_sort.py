@@ -70,3 +70,45 @@ def test_full_size_properties(splat):
     assert int(vo.astype(np.uint64).sum()) == n * (n - 1) // 2       # permutation checksum
     ties = ko[1:] == ko[:-1]
     assert ties.any() and np.all(vo[1:][ties] > vo[:-1][ties])       # stable
+
+
+def test_prefix_beyond_24_bits(splat):
+    """Look-back words keep 24 count bits; a digit value with more than 2^24 keys in front of a tile takes the
+    hi-word path.  20 M keys whose low byte is constant put every prefix of that digit beyond 2^24 from tile 4096 on."""
+    n = 20_000_000
+    rng = np.random.default_rng(11)
+    keys = (rng.integers(0, 1 << 16, n, dtype=np.uint64) << np.uint64(8)) | np.uint64(0x5A)
+    vals = np.arange(n, dtype=np.uint32)
+    ko, vo = splat.sort_pairs_host(keys, vals, 0, 24)
+    assert np.all(ko[1:] >= ko[:-1])
+    np.testing.assert_array_equal(keys[vo], ko)
+    ties = ko[1:] == ko[:-1]
+    assert ties.any() and np.all(vo[1:][ties] > vo[:-1][ties])
+    assert int(vo.astype(np.uint64).sum()) == n * (n - 1) // 2
+
+
+
+def test_status_generation_wrap_over_many_frames(splat, golden_dir):
+    """The renderer never clears the look-back words between frames; their 5-bit generation wraps every 31 frames
+    (the status array is zeroed at the wrap).  70 frames over two cameras must keep giving the same two images."""
+    import os
+
+    from splatapult_b200 import scenes
+
+    g = np.load(os.path.join(golden_dir, "synth_2k_deg3_320x180.npz"))
+    gc = splat.GaussianCloud()
+    gc.SetRawData(g["aos"], True)
+    r = splat.SplatRenderer()
+    assert r.Init(gc, False, False)
+    vp, nf = [0, 0, 320, 180], [scenes.Z_NEAR, scenes.Z_FAR]
+    cams = [g["camera"], scenes.translate(0.7, -0.3, 9.0)]
+    want = []
+    for k in range(70):
+        c = cams[k & 1]
+        r.Sort(c, g["proj"], vp, nf)
+        r.Render(c, g["proj"], vp, nf)
+        fb = r.ReadFramebuffer()
+        if k < 2:
+            want.append(fb.copy())
+        else:
+            np.testing.assert_array_equal(fb, want[k & 1])
