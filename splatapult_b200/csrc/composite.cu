@@ -15,9 +15,10 @@
 //
 // The kernel is instruction-issue bound (ncu: profiles/), not HBM bound, so the design minimises issued
 // instructions per (splat, pixel):
-//   * entries are staged 256 at a time into shared memory with their exp2-folded conic; the gather of the next
-//     chunk's records is issued before the current chunk is evaluated (software pipeline, one barrier per chunk);
-//   * while staging, each entry gets an 8-bit mask of the 8x4 sub-blocks its footprint box can touch; a warp
+//   * entries are staged 256 at a time into shared memory as the coefficients of log2(weight) in the pixel's offset
+//     from the tile centre (5 FFMA + EX2 per pixel); the gather of the next chunk's records is issued before the
+//     current chunk is evaluated (software pipeline, one barrier per chunk);
+//   * while staging, each entry gets an 8-bit mask of the 8x4 sub-blocks its discard ellipse reaches (exact); a warp
 //     ballots the masks of 32 entries at a time and evaluates only its hits -- warp-uniform, no divergence.
 // Pixel centres are at (x+0.5, y+0.5), row 0 is the bottom row (GL window coordinates).
 #include <cuda_fp16.h>

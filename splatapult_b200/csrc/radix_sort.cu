@@ -13,10 +13,12 @@
 //     keys are in registers, and digit 0's comes from the producer (the projection kernel, weighted by each
 //     gaussian's tile count; k_sort_histogram for the stand-alone sorter);
 //   * key tiles are staged into shared memory by the TMA engine (cp.async.bulk + mbarrier, SASS UBLKCP) instead
-//     of per-thread loads; ranks come from warp match / popc ("warp-scan scatter"); the tile is reordered in
-//     shared memory so global stores are digit-run coalesced;
-//   * look-back words carry a 16-bit generation, so nothing is cleared between sorts; element counts are read
-//     from device memory: no host round trip anywhere.
+//     of per-thread loads; ranks come from per-warp peer masks (atomic OR into shared memory, or MATCH.ANY when the
+//     digit is concentrated) + popc ("warp-scan scatter"); the tile is reordered in shared memory so global stores
+//     are digit-run coalesced;
+//   * look-back words are 32 bits wide and carry a 5-bit generation, so nothing is cleared between sorts (the owner
+//     zeroes the array when the generation wraps); element counts are read from device memory: no host round trip;
+//   * the last pass of a frame sort also writes every tile's [begin, end) range (SortWorkspace::tileRanges).
 #include <cstdio>
 #include <cstdlib>
 #include <vector>

@@ -1,4 +1,5 @@
-// renderer.cu -- SplatRenderer: owns the device buffers and enqueues the frame (P -> S1 -> S2 x passes -> ranges -> C).
+// renderer.cu -- SplatRenderer: owns the device buffers and enqueues the frame (default: project_keys -> 4 depth-digit
+// passes on the gaussians -> emit -> tile-digit passes on the instances, the last one writing the tile ranges -> composite).
 //
 // Call protocol and argument meaning follow the reference (src/splatrenderer.h:23-67, src/splatrenderer.cpp:50-343):
 //   Init   : src/splatrenderer.cpp:50-151   (upload the cloud once; no reference to host data afterwards)
