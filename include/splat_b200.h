@@ -70,6 +70,9 @@ SPL_API int spl_device_count(void); /* 0 when no CUDA device is usable */
 SPL_API spl_cloud* spl_cloud_create(int import_full_sh, int export_full_sh);           /* GaussianCloud(Options) :26 */
 SPL_API void spl_cloud_destroy(spl_cloud*);
 SPL_API int spl_cloud_import_ply(spl_cloud*, const char* ply_filename);                /* ImportPly :28 */
+/* ImportPly with the per-vertex decode (sigmoid / exp / quaternion -> Sigma / SH repack, gaussiancloud.cpp:254-361)
+ * run as a CUDA kernel on `device`: same records bit for bit; SPL_ERR_CUDA without a device (no CPU fallback) */
+SPL_API int spl_cloud_import_ply_gpu(spl_cloud*, const char* ply_filename, int device);
 SPL_API int spl_cloud_export_ply(const spl_cloud*, const char* ply_filename);          /* ExportPly :29 */
 SPL_API int spl_cloud_init_debug_cloud(spl_cloud*);                                    /* InitDebugCloud :31 */
 SPL_API int spl_cloud_prune_splats(spl_cloud*, const float origin[3], uint32_t count); /* PruneSplats :34 */
@@ -94,6 +97,9 @@ SPL_API int spl_renderer_init(spl_renderer*, const spl_cloud*, int is_framebuffe
 /* same, from an AoS that is already in device memory (e.g. the destination of an NCCL broadcast) */
 SPL_API int spl_renderer_init_device_aos(spl_renderer*, const void* device_aos, size_t num_gaussians, size_t stride,
                                          int has_full_sh, int is_framebuffer_srgb_enabled);
+/* GaussianCloud::ImportPly + Init in one step, without the host decode and without a host copy of the cloud: the PLY
+ * header is parsed on the host, the raw body is decoded by a CUDA kernel into device memory and packed there */
+SPL_API int spl_renderer_init_ply(spl_renderer*, const char* ply_filename, int import_full_sh, int is_framebuffer_srgb_enabled);
 /* Sort :32-33: cull + project + SH + (tile|depth) key emission + device-wide radix sort + tile ranges */
 SPL_API int spl_renderer_sort(spl_renderer*, const float camera_mat[16], const float proj_mat[16],
                               const float viewport[4], const float near_far[2]);

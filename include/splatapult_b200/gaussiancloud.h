@@ -23,6 +23,9 @@ public:
     explicit GaussianCloud(const Options& options);
 
     bool ImportPly(const std::string& plyFilename);
+    // same result (bit for bit, see csrc/plydecode.cu), with the per-vertex decode run as a CUDA kernel on `device`;
+    // fails without a CUDA device -- ImportPly is the host path
+    bool ImportPlyGpu(const std::string& plyFilename, int device = 0);
     bool ExportPly(const std::string& plyFilename) const;
     void InitDebugCloud();
     // only keep the `numGaussians` splats nearest to `origin`

@@ -35,6 +35,9 @@ public:
     bool Init(std::shared_ptr<GaussianCloud> gaussianCloud, bool isFramebufferSRGBEnabledIn, bool useRgcSortOverrideIn);
     // same, from a reference-layout AoS already resident on the device (NCCL broadcast destination)
     bool InitFromDevice(const void* deviceAos, size_t numGaussians, size_t stride, bool hasFullSH, bool isFramebufferSRGBEnabledIn);
+    // GaussianCloud(opt).ImportPly(file) + Init(cloud, ...) without the host decode: header parsed on the host, the raw
+    // PLY body decoded by a CUDA kernel straight into device memory (same records as ImportPly, csrc/plydecode.cu)
+    bool InitFromPly(const std::string& plyFilename, bool importFullSH, bool isFramebufferSRGBEnabledIn);
 
     // reference signatures (src/splatrenderer.h:32-37); viewport = (x, y, width, height)
     void Sort(const splat::mat4& cameraMat, const splat::mat4& projMat, const splat::vec4& viewport, const splat::vec2& nearFar);

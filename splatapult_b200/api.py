@@ -65,6 +65,8 @@ _SIGNATURES = [
     ("spl_cloud_create", C.c_void_p, [C.c_int, C.c_int]),
     ("spl_cloud_destroy", None, [C.c_void_p]),
     ("spl_cloud_import_ply", C.c_int, [C.c_void_p, C.c_char_p]),
+    ("spl_cloud_import_ply_gpu", C.c_int, [C.c_void_p, C.c_char_p, C.c_int]),
+    ("spl_renderer_init_ply", C.c_int, [C.c_void_p, C.c_char_p, C.c_int, C.c_int]),
     ("spl_cloud_export_ply", C.c_int, [C.c_void_p, C.c_char_p]),
     ("spl_cloud_init_debug_cloud", C.c_int, [C.c_void_p]),
     ("spl_cloud_prune_splats", C.c_int, [C.c_void_p, _FP, C.c_uint32]),
@@ -171,6 +173,10 @@ class GaussianCloud:
     def ImportPly(self, ply_filename: str) -> bool:
         return lib().spl_cloud_import_ply(self._h, os.fsencode(ply_filename)) == 0
 
+    def ImportPlyGpu(self, ply_filename: str, device: int = 0) -> bool:
+        """ImportPly with the per-vertex decode run as a CUDA kernel (same records bit for bit); False without a GPU."""
+        return lib().spl_cloud_import_ply_gpu(self._h, os.fsencode(ply_filename), int(device)) == 0
+
     def ExportPly(self, ply_filename: str) -> bool:
         return lib().spl_cloud_export_ply(self._h, os.fsencode(ply_filename)) == 0
 
@@ -258,6 +264,10 @@ class SplatRenderer:
     # --- explicit replacements for implicit GL state
     def InitFromDevice(self, device_ptr: int, num_gaussians: int, stride: int, has_full_sh: bool, srgb: bool = False) -> None:
         _check(lib().spl_renderer_init_device_aos(self._h, C.c_void_p(device_ptr), num_gaussians, stride, int(has_full_sh), int(srgb)))
+
+    def InitFromPly(self, ply_filename: str, import_full_sh: bool = True, srgb: bool = False) -> None:
+        """ImportPly + Init without the host decode: the PLY body is decoded on the device and packed there."""
+        _check(lib().spl_renderer_init_ply(self._h, os.fsencode(ply_filename), int(import_full_sh), int(srgb)))
 
     def Framebuffer(self):
         """(device_ptr, width, height, row_pitch_bytes, fb_format) of the last Render."""

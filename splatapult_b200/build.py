@@ -30,6 +30,7 @@ CXX_FLAGS = ["-std=c++17", "-O2", "-fPIC", "-ffp-contract=off", "-fvisibility=hi
 CU_SOURCES = {
     "pack.cu": [],
     "project.cu": ["-fmad=false"],
+    "plydecode.cu": ["-fmad=false"],
     "radix_sort.cu": [],
     "binsort.cu": [],
     "composite.cu": [],

@@ -66,6 +66,13 @@ int spl_cloud_import_ply(spl_cloud* c, const char* path)
     if (!c->gc->ImportPly(path)) return set_error(SPL_ERR_IO, c->gc->GetError());
     return SPL_OK;
 }
+int spl_cloud_import_ply_gpu(spl_cloud* c, const char* path, int device)
+{
+    if (!c || !path) return set_error(SPL_ERR_ARG, "null argument");
+    if (spl_device_count() < 1) return set_error(SPL_ERR_CUDA, "no CUDA device: spl_cloud_import_ply_gpu has no CPU fallback (use spl_cloud_import_ply)");
+    if (!c->gc->ImportPlyGpu(path, device)) return set_error(SPL_ERR_IO, c->gc->GetError());
+    return SPL_OK;
+}
 int spl_cloud_export_ply(const spl_cloud* c, const char* path)
 {
     if (!c || !path) return set_error(SPL_ERR_ARG, "null argument");
@@ -130,6 +137,11 @@ int spl_renderer_init_device_aos(spl_renderer* h, const void* device_aos, size_t
 {
     if (!h || (!device_aos && n)) return set_error(SPL_ERR_ARG, "null argument");
     return from_renderer(h, h->r.InitFromDevice(device_aos, n, stride, has_full_sh != 0, srgb != 0));
+}
+int spl_renderer_init_ply(spl_renderer* h, const char* path, int import_full_sh, int srgb)
+{
+    if (!h || !path) return set_error(SPL_ERR_ARG, "null argument");
+    return from_renderer(h, h->r.InitFromPly(path, import_full_sh != 0, srgb != 0));
 }
 int spl_renderer_sort(spl_renderer* h, const float cam[16], const float proj[16], const float vp[4], const float nf[2])
 {

@@ -15,6 +15,7 @@
 #include <numeric>
 #include <vector>
 
+#include "plydecode.h"
 #include "splatapult_b200/ply.h"
 
 namespace
@@ -154,6 +155,29 @@ void GaussianCloud::InitAttribs()
     }
 }
 
+namespace
+{
+// name -> (type, offset) lookups of the INRIA schema; a missing required property only reads as zero
+struct PlyProps
+{
+    BinaryAttribute px, py, pz, opacity, dc[3], rest[45], scale[3], rot[4];
+    bool fullSH = false;
+};
+PlyProps LookupProps(const Ply& ply, bool wantFullSH)
+{
+    PlyProps p;
+    ply.GetProperty("x", p.px); ply.GetProperty("y", p.py); ply.GetProperty("z", p.pz);
+    ply.GetProperty("opacity", p.opacity);
+    for (int i = 0; i < 3; i++) ply.GetProperty("f_dc_" + std::to_string(i), p.dc[i]);
+    for (int i = 0; i < 3; i++) ply.GetProperty("scale_" + std::to_string(i), p.scale[i]);
+    for (int i = 0; i < 4; i++) ply.GetProperty("rot_" + std::to_string(i), p.rot[i]);
+    p.fullSH = wantFullSH;
+    for (int i = 0; p.fullSH && i < 45; i++)
+        if (!ply.GetProperty("f_rest_" + std::to_string(i), p.rest[i])) p.fullSH = false;  // all 45 or none
+    return p;
+}
+}  // namespace
+
 bool GaussianCloud::ImportPly(const std::string& plyFilename)
 {
     std::ifstream file(plyFilename, std::ios::binary);
@@ -161,17 +185,8 @@ bool GaussianCloud::ImportPly(const std::string& plyFilename)
     Ply ply;
     if (!ply.Parse(file)) { error = "error parsing ply file \"" + plyFilename + "\": " + ply.GetError(); return false; }
 
-    // name -> (type, offset) lookups happen once; a missing required property only reads as zero
-    BinaryAttribute px, py, pz, opacity, dc[3], rest[45], scale[3], rot[4];
-    ply.GetProperty("x", px); ply.GetProperty("y", py); ply.GetProperty("z", pz);
-    ply.GetProperty("opacity", opacity);
-    for (int i = 0; i < 3; i++) ply.GetProperty("f_dc_" + std::to_string(i), dc[i]);
-    for (int i = 0; i < 3; i++) ply.GetProperty("scale_" + std::to_string(i), scale[i]);
-    for (int i = 0; i < 4; i++) ply.GetProperty("rot_" + std::to_string(i), rot[i]);
-    hasFullSH = opt.importFullSH;
-    for (int i = 0; hasFullSH && i < 45; i++)
-        if (!ply.GetProperty("f_rest_" + std::to_string(i), rest[i])) hasFullSH = false;  // all 45 or none
-
+    const PlyProps P = LookupProps(ply, opt.importFullSH);
+    hasFullSH = P.fullSH;
     auto readf = [](const BinaryAttribute& a, const void* v) { return a.type == BinaryAttribute::Type::Float ? a.Read<float>(v) : 0.0f; };
 
     InitAttribs();
@@ -182,22 +197,65 @@ bool GaussianCloud::ImportPly(const std::string& plyFilename)
     const size_t vsize = ply.GetVertexSize();
     for (size_t n = 0; n < numGaussians; n++, rec += recFloats, v += vsize)
     {
-        rec[kPos + 0] = readf(px, v);
-        rec[kPos + 1] = readf(py, v);
-        rec[kPos + 2] = readf(pz, v);
-        rec[kPos + 3] = 1.0f / (1.0f + expf(-readf(opacity, v)));
+        rec[kPos + 0] = readf(P.px, v);
+        rec[kPos + 1] = readf(P.py, v);
+        rec[kPos + 2] = readf(P.pz, v);
+        rec[kPos + 3] = 1.0f / (1.0f + expf(-readf(P.opacity, v)));
         for (int c = 0; c < 3; c++)
         {
-            *ShSlot(rec, c, 0) = readf(dc[c], v);
+            *ShSlot(rec, c, 0) = readf(P.dc[c], v);
             if (hasFullSH)
-                for (int k = 1; k < 16; k++) *ShSlot(rec, c, k) = readf(rest[15 * c + k - 1], v);
+                for (int k = 1; k < 16; k++) *ShSlot(rec, c, k) = readf(P.rest[15 * c + k - 1], v);
             // base layout: the three degree-1 slots stay 0 (Allocate zero-fills)
         }
-        const float s[3] = {expf(readf(scale[0], v)), expf(readf(scale[1], v)), expf(readf(scale[2], v))};
-        const float q[4] = {readf(rot[0], v), readf(rot[1], v), readf(rot[2], v), readf(rot[3], v)};
+        const float s[3] = {expf(readf(P.scale[0], v)), expf(readf(P.scale[1], v)), expf(readf(P.scale[2], v))};
+        const float q[4] = {readf(P.rot[0], v), readf(P.rot[1], v), readf(P.rot[2], v), readf(P.rot[3], v)};
         CovarianceFromRotScale(q, s, rec + kCov);
     }
     return true;
+}
+
+// Same result as ImportPly, with the per-vertex decode done by a CUDA kernel (csrc/plydecode.cu): header parsed
+// here, raw body copied to the device, the decoded AoS copied back.  SURVEY 8f-f4.  No CPU fallback: without a
+// CUDA device this returns false.
+bool GaussianCloud::ImportPlyGpu(const std::string& plyFilename, int device)
+{
+    std::ifstream file(plyFilename, std::ios::binary);
+    if (!file.is_open()) { error = "failed to open " + plyFilename; return false; }
+    Ply ply;
+    if (!ply.Parse(file)) { error = "error parsing ply file \"" + plyFilename + "\": " + ply.GetError(); return false; }
+    bool fullSH = false;
+    splat::PlyDecodeLayout layout;
+    splat::make_ply_decode_layout(ply, opt.importFullSH, &layout, &fullSH);
+    hasFullSH = fullSH;
+    InitAttribs();
+    Allocate(ply.GetVertexCount(), (hasFullSH ? kFullFloats : kBaseFloats) * sizeof(float));
+    std::string err;
+    if (!splat::decode_ply_on_device(ply.GetData(), numGaussians, ply.GetVertexSize(), layout, hasFullSH, device, nullptr,
+                                     static_cast<float*>(data.get()), nullptr, &err))
+    {
+        error = "GPU ply decode of \"" + plyFilename + "\" failed: " + err;
+        return false;
+    }
+    return true;
+}
+
+void splat::make_ply_decode_layout(const Ply& ply, bool wantFullSH, splat::PlyDecodeLayout* out, bool* fullSHOut)
+{
+    const PlyProps P = LookupProps(ply, wantFullSH);
+    auto off = [](const BinaryAttribute& a) { return a.type == BinaryAttribute::Type::Float ? (int)a.offset : -1; };
+    splat::PlyDecodeLayout& L = *out;
+    L.pos[0] = off(P.px); L.pos[1] = off(P.py); L.pos[2] = off(P.pz);
+    L.opacity = off(P.opacity);
+    for (int i = 0; i < 3; i++) { L.dc[i] = off(P.dc[i]); L.scale[i] = off(P.scale[i]); }
+    for (int i = 0; i < 4; i++) L.rot[i] = off(P.rot[i]);
+    for (int i = 0; i < 45; i++) L.rest[i] = P.fullSH ? off(P.rest[i]) : -1;
+    bool aligned = ply.GetVertexSize() % 4 == 0;
+    const int* all = &L.pos[0];
+    for (size_t i = 0; aligned && i < (sizeof(splat::PlyDecodeLayout) / sizeof(int)) - 1; i++)
+        if (all[i] >= 0 && all[i] % 4 != 0) aligned = false;
+    L.aligned = aligned ? 1 : 0;
+    *fullSHOut = P.fullSH;
 }
 
 bool GaussianCloud::ExportPly(const std::string& plyFilename) const

@@ -13,10 +13,13 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <fstream>
 #include <vector>
 
 #include "kernels.h"
+#include "plydecode.h"
 #include "splat_b200.h"
+#include "splatapult_b200/ply.h"
 
 namespace splat
 {
@@ -644,6 +647,29 @@ bool SplatRenderer::Init(std::shared_ptr<GaussianCloud> gaussianCloud, bool isFr
 bool SplatRenderer::InitFromDevice(const void* deviceAos, size_t numGaussians, size_t stride, bool hasFullSH, bool isFramebufferSRGBEnabledIn)
 {
     FORWARD(impl->initFromDevice(deviceAos, numGaussians, stride, hasFullSH, isFramebufferSRGBEnabledIn));
+}
+
+bool SplatRenderer::InitFromPly(const std::string& plyFilename, bool importFullSH, bool isFramebufferSRGBEnabledIn)
+{
+    auto failWith = [&](int code, const std::string& msg) { status = code; error = msg; return false; };
+    std::ifstream file(plyFilename, std::ios::binary);
+    if (!file.is_open()) return failWith(SPL_ERR_IO, "failed to open " + plyFilename);
+    Ply ply;
+    if (!ply.Parse(file)) return failWith(SPL_ERR_IO, "error parsing ply file \"" + plyFilename + "\": " + ply.GetError());
+    splat::PlyDecodeLayout layout;
+    bool fullSH = false;
+    splat::make_ply_decode_layout(ply, importFullSH, &layout, &fullSH);
+    if (int rc = impl->begin()) { status = rc; error = impl->error; return false; }
+    void* dAos = nullptr;
+    std::string err;
+    if (!splat::decode_ply_on_device(ply.GetData(), ply.GetVertexCount(), ply.GetVertexSize(), layout, fullSH, impl->device, impl->stream, nullptr, &dAos,
+                                     &err))
+        return failWith(SPL_ERR_CUDA, "GPU ply decode of \"" + plyFilename + "\" failed: " + err);
+    const int rc = impl->initFromDevice(dAos, ply.GetVertexCount(), fullSH ? 244 : 100, fullSH, isFramebufferSRGBEnabledIn);
+    splat::free_decoded_aos(dAos);
+    status = rc;
+    error = impl->error;
+    return rc == 0;
 }
 
 void SplatRenderer::Sort(const splat::mat4& cameraMat, const splat::mat4& projMat, const splat::vec4& viewport, const splat::vec2& nearFar)
