@@ -323,10 +323,12 @@ def run_ours(args, rank, local_rank, world):
         split = int(st.sort_mode) == api.SORT_LSD  # depth digits sorted on the N gaussians, tile digits on the D instances
         d_passes = int(st.sort_passes) - 4 if split else int(st.sort_passes)  # onesweep passes that run on the D instances
         if split:
-            # project_keys writes 12 B key/id + 8 B rectangle per gaussian instead of 12 B per instance;
-            # stage 1 = 4 depth-digit passes on N pairs (24 N each) + expansion (20 N in, 12 D out)
-            ab["project"] = ab["project"] - 12 * d + 20 * n
-            ab["depth_sort_emit"] = 4 * 24 * n + 20 * n + 12 * d
+            # project_keys writes a u32 key + u32 id + 8 B rectangle per gaussian instead of 12 B per instance;
+            # stage 1 = 4 depth-digit passes on N (u32, u32) pairs (16 N each) + expansion (4 N ids + 8 N rectangles in,
+            # (u32 tile, u32 id) = 8 D out); the tile-digit passes move 8-byte instances (16 D per pass)
+            ab["project"] = ab["project"] - 12 * d + 16 * n
+            ab["depth_sort_emit"] = 4 * 16 * n + 12 * n + 8 * d
+            ab["sort_pass"] = 16 * d
             ab["frame"] = ab["project"] + ab["depth_sort_emit"] + d_passes * ab["sort_pass"] + ab["tile_ranges"] + ab["composite"]
             stage = {"project": stages[0], "depth_sort_emit": stages[1], "tile_sort_passes_total": stages[2],
                      "composite": stages[4], "frame": stages[7]}
@@ -342,10 +344,20 @@ def run_ours(args, rank, local_rank, world):
     dom = max(cand, key=lambda k: cand[k][0])
     dom_total, dom_bytes, dom_launch_ms = cand[dom]
     achieved = dom_bytes / (dom_launch_ms * 1e-3) / 1e9 if dom_launch_ms > 0 else 0.0
-    traffic = None
+    traffic, issue = None, None
     try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
-            traffic = json.load(f).get(args.workload, {}).get(dom)
+            prof = json.load(f)
+        traffic = prof.get(args.workload, {}).get(dom)
+        # the dominant kernel of this path is instruction-issue bound, not HBM bound: also report how close it is to
+        # that bound -- warp instructions per launch (ncu smsp__inst_executed.sum, a property of the workload) over the
+        # live launch time, per SM sub-partition (peak 1 warp instruction per cycle)
+        wi = prof.get("warp_instructions", {}).get(args.workload, {}).get(dom)
+        clk = clocks.summary().get("sm_mhz")
+        if wi and clk and dom_launch_ms > 0:
+            smsps = torch.cuda.get_device_properties(dev).multi_processor_count * 4
+            issue = {"warp_instructions_per_launch": wi, "ipc_per_smsp": wi / (dom_launch_ms * 1e-3 * clk * 1e6 * smsps), "peak": 1.0,
+                     "source": "ncu smsp__inst_executed.sum (profiles/r1j_ncu_current.md) / live launch time / (SMSPs x sampled SM clock)"}
     except Exception:
         pass
 
@@ -370,7 +382,7 @@ def run_ours(args, rank, local_rank, world):
                                 "note": "informational: same loop, reading the 8-bit presented frame (RenderDesktop blit) instead of the float target"},
         "gpu_launches": int(st.kernel_launches) * args.steps,
         "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": dom_bytes,
+                     "traffic": traffic, "issue": issue, "peak_source": peak_src, "algorithmic_bytes_per_launch": dom_bytes,
                      "launch_ms": dom_launch_ms, "share_of_step": dom_total / stages[7] if stages[7] > 0 else None,
                      "frame": {"algorithmic_bytes": ab["frame"], "achieved": ab["frame"] / (stages[7] * 1e-3) / 1e9 if stages[7] > 0 else None,
                                "frac": ab["frame"] / (stages[7] * 1e-3) / 1e9 / peak if stages[7] > 0 else None}},

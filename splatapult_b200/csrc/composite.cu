@@ -38,26 +38,28 @@ constexpr int kSubRows = kTileSize / kSubH;          // 4
 // ---------------------------------------------------------------------------------------------------
 // tile ranges: [begin, end) of each tile's run in the sorted key array
 // ---------------------------------------------------------------------------------------------------
-__global__ void k_tile_ranges(const unsigned long long* __restrict__ keys, const uint32_t* __restrict__ nDevice, uint2* __restrict__ ranges,
+template <typename KeyT>
+__global__ void k_tile_ranges(const KeyT* __restrict__ keys, int keyShift, const uint32_t* __restrict__ nDevice, uint2* __restrict__ ranges,
                               uint32_t numTiles)
 {
     const uint32_t n = *nDevice;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
     {
-        const uint32_t tile = (uint32_t)(keys[i] >> 32);
+        const uint32_t tile = (uint32_t)(keys[i] >> keyShift);
         if (tile >= numTiles) continue;  // cannot happen for keys this library emits
-        if (i == 0 || (uint32_t)(keys[i - 1] >> 32) != tile) ranges[tile].x = i;
-        if (i == n - 1 || (uint32_t)(keys[i + 1] >> 32) != tile) ranges[tile].y = i + 1;
+        if (i == 0 || (uint32_t)(keys[i - 1] >> keyShift) != tile) ranges[tile].x = i;
+        if (i == n - 1 || (uint32_t)(keys[i + 1] >> keyShift) != tile) ranges[tile].y = i + 1;
     }
 }
 
-cudaError_t launch_tile_ranges(const unsigned long long* sortedKeys, const uint32_t* nDevice, uint64_t capacity, uint2* ranges, uint32_t numTiles,
+cudaError_t launch_tile_ranges(const void* sortedKeys, int keyBytes, const uint32_t* nDevice, uint64_t capacity, uint2* ranges, uint32_t numTiles,
                                int numSMs, cudaStream_t stream)
 {
     cudaError_t e = cudaMemsetAsync(ranges, 0, (size_t)numTiles * sizeof(uint2), stream);
     if (e != cudaSuccess) return e;
     const uint32_t blocks = (uint32_t)max(1ull, min((unsigned long long)numSMs * 8ull, (unsigned long long)((capacity + 255) / 256)));
-    k_tile_ranges<<<blocks, 256, 0, stream>>>(sortedKeys, nDevice, ranges, numTiles);
+    if (keyBytes == 4) k_tile_ranges<uint32_t><<<blocks, 256, 0, stream>>>(static_cast<const uint32_t*>(sortedKeys), 0, nDevice, ranges, numTiles);
+    else k_tile_ranges<unsigned long long><<<blocks, 256, 0, stream>>>(static_cast<const unsigned long long*>(sortedKeys), 32, nDevice, ranges, numTiles);
     return cudaGetLastError();
 }
 

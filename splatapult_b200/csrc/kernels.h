@@ -21,13 +21,13 @@ uint32_t project_num_blocks(uint32_t n);
 cudaError_t launch_project(const PackedCloud& cloud, const FrameConstants& fc, ProjRecord* rec, unsigned long long* keys, uint32_t* vals,
                            FrameCounters* ctr, unsigned long long* scanState, uint32_t capacity, uint32_t* digit0Hist, cudaStream_t stream);
 
-// default LSD path: (1) project + one (depthKey, id) pair and an 8-byte tile rectangle per gaussian; after the depth
-// digits have been sorted on those N pairs, (2) expand the sorted list into (tile << 32 | depthKey, id) instances in
+// default LSD path: (1) project + one (u32 depthKey, id) pair and an 8-byte tile rectangle per gaussian; after the
+// depth digits have been sorted on those N pairs, (2) expand the sorted id list into (u32 tile id, id) instances in
 // depth order (scan + coalesced emission) and leave the histogram of the first tile digit in tileDigitHist
-cudaError_t launch_project_keys(const PackedCloud& cloud, const FrameConstants& fc, ProjRecord* rec, unsigned long long* keys, uint32_t* vals,
+cudaError_t launch_project_keys(const PackedCloud& cloud, const FrameConstants& fc, ProjRecord* rec, uint32_t* keys, uint32_t* vals,
                                 uint2* side, FrameCounters* ctr, uint32_t* digit0Hist, cudaStream_t stream);
-cudaError_t launch_emit_sorted(const unsigned long long* sortedKeys, const uint32_t* sortedVals, const uint2* side, uint32_t n,
-                               const FrameConstants& fc, unsigned long long* keys, uint32_t* vals, FrameCounters* ctr,
+cudaError_t launch_emit_sorted(const uint32_t* sortedVals, const uint2* side, uint32_t n,
+                               const FrameConstants& fc, uint32_t* keys, uint32_t* vals, FrameCounters* ctr,
                                unsigned long long* scanState, uint32_t capacity, uint32_t* tileDigitHist, cudaStream_t stream);
 
 cudaError_t launch_project_bin(const PackedCloud& cloud, const FrameConstants& fc, ProjRecord* rec, uint4* side, uint32_t* tileCount,
@@ -74,8 +74,15 @@ cudaError_t launch_sort_histogram(const unsigned long long* keysA, const uint32_
 cudaError_t launch_sort_passes(unsigned long long* keysA, uint32_t* valsA, unsigned long long* keysB, uint32_t* valsB, const uint32_t* nDevice,
                                uint64_t capacity, int beginBit, int endBit, const SortWorkspace& ws, int numSMs, cudaStream_t stream);
 
+// same passes on (u32 key, u32 value) pairs, endBit <= 32: 8 bytes per element, 4 CTAs per SM.  The frame's default path
+// sorts u32 depth keys on the gaussians and bare u32 tile ids on the instances (the depth order survives the tile passes
+// because they are stable, so the instances need not carry the depth key).  With ws.tileRanges the tile id is the key.
+cudaError_t launch_sort_passes32(uint32_t* keysA, uint32_t* valsA, uint32_t* keysB, uint32_t* valsB, const uint32_t* nDevice, uint64_t capacity,
+                                 int beginBit, int endBit, const SortWorkspace& ws, int numSMs, cudaStream_t stream);
+
 // ---- composite.cu
-cudaError_t launch_tile_ranges(const unsigned long long* sortedKeys, const uint32_t* nDevice, uint64_t capacity, uint2* ranges,
+// keyShift: where the tile id sits in a key (32: tile << 32 | depthKey, u64; 0 with keyBytes 4: bare u32 tile ids)
+cudaError_t launch_tile_ranges(const void* sortedKeys, int keyBytes, const uint32_t* nDevice, uint64_t capacity, uint2* ranges,
                                uint32_t numTiles, int numSMs, cudaStream_t stream);
 // ids: gaussian id of list entry k is ids[k * idStrideWords] (1: u32 payload array of the LSD sort, 2: low word of the
 // binned sort's u64 (depthKey << 32 | id) pairs)

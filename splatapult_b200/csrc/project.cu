@@ -403,8 +403,8 @@ k_project(const PackedCloud cloud, const __grid_constant__ FrameConstants fc, Pr
 }
 
 // ---------------------------------------------------------------------------------------------------
-// default LSD path, step 2: expand the depth-sorted gaussian list into (tile << 32 | depthKey, id) instances, in
-// depth order.  Same scan + look-back + warp-cooperative emission as k_project, but every thread carries
+// default LSD path, step 2: expand the depth-sorted gaussian list into (tile id, gaussian id) instances, in depth
+// order -- the instances do not carry the depth key: the tile-digit passes that follow are stable.  Same scan + look-back + warp-cooperative emission as k_project, but every thread carries
 // kEmitRounds entries (entry j = cta * 1024 + round * 256 + tid, so loads stay coalesced and the emission order is
 // the list order): a quarter of the CTAs means a quarter of the links in the look-back chain.  With one entry per
 // thread the walkers (32 predecessors per L2 round trip) were slower than the rate at which new CTAs start, so the
@@ -413,15 +413,15 @@ k_project(const PackedCloud cloud, const __grid_constant__ FrameConstants fc, Pr
 constexpr int kEmitRounds = 4;
 
 __global__ void __launch_bounds__(kProjThreads)
-k_emit_sorted(const unsigned long long* __restrict__ sortedKeys, const uint32_t* __restrict__ sortedVals, const uint2* __restrict__ side,
-              uint32_t nSorted, uint32_t tilesX, unsigned long long* __restrict__ keys, uint32_t* __restrict__ vals,
+k_emit_sorted(const uint32_t* __restrict__ sortedVals, const uint2* __restrict__ side,
+              uint32_t nSorted, uint32_t tilesX, uint32_t* __restrict__ keys, uint32_t* __restrict__ vals,
               FrameCounters* __restrict__ ctr, unsigned long long* __restrict__ scanState, uint32_t capacity, uint32_t* __restrict__ tileDigitHist)
 {
     constexpr int kWarps = kProjThreads / 32;
     __shared__ uint32_t sBlockId;
     __shared__ uint32_t sWarpTotal[kEmitRounds][kWarps];
     __shared__ unsigned long long sBlockBase;
-    __shared__ uint32_t sDigit0[kRadixSize];  // histogram of the first tile digit (bits 32..39), one count per instance
+    __shared__ uint32_t sDigit0[kRadixSize];  // histogram of the first tile digit (low byte of the tile id), one count per instance
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid == 0) sBlockId = atomicAdd(&ctr->projectTicket, 1u);  // dynamic id: predecessors are resident or done
@@ -429,12 +429,12 @@ k_emit_sorted(const unsigned long long* __restrict__ sortedKeys, const uint32_t*
     __syncthreads();
     const uint32_t vbid = sBlockId;
 
-    uint32_t count[kEmitRounds], rect[kEmitRounds], refKey[kEmitRounds], id[kEmitRounds], incl[kEmitRounds];
+    uint32_t count[kEmitRounds], rect[kEmitRounds], id[kEmitRounds], incl[kEmitRounds];
 #pragma unroll
     for (int r = 0; r < kEmitRounds; r++)
     {
         const uint32_t j = (vbid * kEmitRounds + r) * kProjThreads + tid;
-        count[r] = 0; rect[r] = 0; refKey[r] = 0; id[r] = 0;
+        count[r] = 0; rect[r] = 0; id[r] = 0;
         if (j < nSorted)
         {
             id[r] = __ldg(sortedVals + j);
@@ -442,7 +442,6 @@ k_emit_sorted(const unsigned long long* __restrict__ sortedKeys, const uint32_t*
             const uint32_t w = sd.y & 0xffffu, h = sd.y >> 16;
             count[r] = w * h;
             rect[r] = (sd.x & 0xffffu) | ((sd.x >> 16) << 10) | ((w ? w - 1 : 0) << 20);
-            refKey[r] = (uint32_t)__ldg(sortedKeys + j);
         }
     }
 #pragma unroll
@@ -548,7 +547,6 @@ k_emit_sorted(const unsigned long long* __restrict__ sortedKeys, const uint32_t*
             const uint32_t oBase = __shfl_sync(0xffffffffu, wexE, owner);
             const uint32_t oOff = __shfl_sync(0xffffffffu, gOff, owner);
             const uint32_t oRect = __shfl_sync(0xffffffffu, rect[r], owner);
-            const uint32_t oKey = __shfl_sync(0xffffffffu, refKey[r], owner);
             const uint32_t oId = __shfl_sync(0xffffffffu, id[r], owner);
             if (j < T)
             {
@@ -556,7 +554,7 @@ k_emit_sorted(const unsigned long long* __restrict__ sortedKeys, const uint32_t*
                 const uint32_t w = (oRect >> 20) + 1, x0 = oRect & 1023u, y0 = (oRect >> 10) & 1023u;
                 const uint32_t row = k / w, col = k - row * w;
                 const uint32_t tile = (y0 + row) * tilesX + (x0 + col);
-                keys[oOff + k] = ((unsigned long long)tile << 32) | oKey;
+                keys[oOff + k] = tile;
                 vals[oOff + k] = oId;
                 if (tileDigitHist) smem_red_add(&sDigit0[tile & (kRadixSize - 1)], 1u);
             }
@@ -581,7 +579,7 @@ k_emit_sorted(const unsigned long long* __restrict__ sortedKeys, const uint32_t*
 template <int SH_MODE>
 __global__ void __launch_bounds__(kProjThreads)
 k_project_keys(const PackedCloud cloud, const __grid_constant__ FrameConstants fc, ProjRecord* __restrict__ rec,
-               unsigned long long* __restrict__ keys, uint32_t* __restrict__ vals, uint2* __restrict__ side, FrameCounters* __restrict__ ctr,
+               uint32_t* __restrict__ keys, uint32_t* __restrict__ vals, uint2* __restrict__ side, FrameCounters* __restrict__ ctr,
                uint32_t* __restrict__ digit0Hist)
 {
     __shared__ uint32_t sDigit0[kRadixSize];
@@ -748,7 +746,7 @@ cudaError_t launch_project(const PackedCloud& cloud, const FrameConstants& fc, P
     return cudaGetLastError();
 }
 
-cudaError_t launch_project_keys(const PackedCloud& cloud, const FrameConstants& fc, ProjRecord* rec, unsigned long long* keys, uint32_t* vals,
+cudaError_t launch_project_keys(const PackedCloud& cloud, const FrameConstants& fc, ProjRecord* rec, uint32_t* keys, uint32_t* vals,
                                 uint2* side, FrameCounters* ctr, uint32_t* digit0Hist, cudaStream_t stream)
 {
     const uint32_t blocks = project_num_blocks(cloud.n);
@@ -762,14 +760,14 @@ cudaError_t launch_project_keys(const PackedCloud& cloud, const FrameConstants& 
     return cudaGetLastError();
 }
 
-cudaError_t launch_emit_sorted(const unsigned long long* sortedKeys, const uint32_t* sortedVals, const uint2* side, uint32_t n,
-                               const FrameConstants& fc, unsigned long long* keys, uint32_t* vals, FrameCounters* ctr,
+cudaError_t launch_emit_sorted(const uint32_t* sortedVals, const uint2* side, uint32_t n,
+                               const FrameConstants& fc, uint32_t* keys, uint32_t* vals, FrameCounters* ctr,
                                unsigned long long* scanState, uint32_t capacity, uint32_t* tileDigitHist, cudaStream_t stream)
 {
     const uint32_t perCta = kProjThreads * kEmitRounds;
     const uint32_t blocks = (n + perCta - 1) / perCta;  // <= project_num_blocks(n): scanState is large enough
     if (blocks == 0) return cudaSuccess;
-    k_emit_sorted<<<blocks, kProjThreads, 0, stream>>>(sortedKeys, sortedVals, side, n, (uint32_t)fc.tilesX, keys, vals, ctr, scanState, capacity,
+    k_emit_sorted<<<blocks, kProjThreads, 0, stream>>>(sortedVals, side, n, (uint32_t)fc.tilesX, keys, vals, ctr, scanState, capacity,
                                                        tileDigitHist);
     return cudaGetLastError();
 }

@@ -30,7 +30,8 @@ namespace splat
 
 constexpr int kHistThreads = 256;
 
-__device__ __forceinline__ uint32_t digit_of(unsigned long long key, int shift, uint32_t mask) { return (uint32_t)(key >> shift) & mask; }
+template <typename KeyT>
+__device__ __forceinline__ uint32_t digit_of(KeyT key, int shift, uint32_t mask) { return (uint32_t)(key >> shift) & mask; }
 __host__ __device__ __forceinline__ uint32_t digit_mask(int shift, int endBit)
 {
     const int bits = endBit - shift;
@@ -118,12 +119,14 @@ k_sort_histogram(const unsigned long long* __restrict__ keys, const uint32_t* __
 // S2: one scatter pass (onesweep): rank in tile, look back for the tile's global digit offsets, scatter;
 //     also accumulates the NEXT pass's digit histogram
 // ---------------------------------------------------------------------------------------------------
-template <int KPT>
+// KeyT = unsigned long long (tile << 32 | depthKey, and the stand-alone sorter) or uint32_t (the frame's depth keys on
+// the gaussians and bare tile ids on the instances: 8 bytes per element instead of 12, 4 CTAs per SM instead of 3)
+template <int KPT, typename KeyT>
 struct SortSmem
 {
     static constexpr int kTile = kSortThreads * KPT;
     static constexpr int kWarps = kSortThreads / 32;
-    unsigned long long keys[kTile];               // TMA destination; reused for the digit-ordered tile
+    KeyT keys[kTile];                             // TMA destination; reused for the digit-ordered tile
     uint32_t vals[kTile];                         // TMA destination; reused for the digit-ordered payloads
     uint32_t warpCount[kWarps][kRadixSize];       // per-warp digit counters -> exclusive prefix over warps
     uint32_t matchMask[kWarps][kRadixSize];       // atomic-OR matching: lanes of the warp holding each digit (zero between rows)
@@ -154,15 +157,15 @@ struct SortSmem
 #define TLREC(k) ((void)0)
 #endif
 
-template <int KPT>
-__global__ void __launch_bounds__(kSortThreads, KPT == 16 ? 3 : 5)
-k_sort_onesweep(const unsigned long long* __restrict__ keysIn, const uint32_t* __restrict__ valsIn, unsigned long long* __restrict__ keysOut,
+template <int KPT, typename KeyT>
+__global__ void __launch_bounds__(kSortThreads, KPT == 16 ? (sizeof(KeyT) == 4 ? 4 : 3) : 5)
+k_sort_onesweep(const KeyT* __restrict__ keysIn, const uint32_t* __restrict__ valsIn, KeyT* __restrict__ keysOut,
                 uint32_t* __restrict__ valsOut, const uint32_t* __restrict__ nDevice, int shift, uint32_t mask, int nextShift, uint32_t nextMask,
                 const uint32_t* __restrict__ histogram, uint32_t* __restrict__ histogramNext, unsigned long long* __restrict__ status,
                 uint32_t* __restrict__ ticket, uint32_t gen, unsigned long long* tl, uint2* __restrict__ tileRanges, uint32_t numRangeTiles,
-                uint32_t statusTiles)
+                uint32_t statusTiles, int rangeShift)
 {
-    using Smem = SortSmem<KPT>;
+    using Smem = SortSmem<KPT, KeyT>;
     constexpr int kTile = Smem::kTile;
     constexpr int kWarps = Smem::kWarps;
     extern __shared__ __align__(128) unsigned char smemRaw[];
@@ -231,7 +234,7 @@ k_sort_onesweep(const unsigned long long* __restrict__ keysIn, const uint32_t* _
 
         if (tid == 0)
         {
-            const uint32_t kb = (nValid * 8u + 15u) & ~15u, vb = (nValid * 4u + 15u) & ~15u;
+            const uint32_t kb = (nValid * (uint32_t)sizeof(KeyT) + 15u) & ~15u, vb = (nValid * 4u + 15u) & ~15u;
             fence_proxy_async();
             mbar_expect_tx(&s.bar, kb + vb);
             bulk_g2s(s.keys, keysIn + (size_t)tile * kTile, kb, &s.bar);
@@ -242,13 +245,13 @@ k_sort_onesweep(const unsigned long long* __restrict__ keysIn, const uint32_t* _
         TLREC(1);
 
         // ---- rank: warp w owns items [w*KPT*32, (w+1)*KPT*32), item j of a lane = base + j*32 + lane (memory order)
-        unsigned long long key[KPT];
+        KeyT key[KPT];
         uint16_t pos[KPT];
 #pragma unroll
         for (int j = 0; j < KPT; j++)
         {
             const uint32_t idx = warp * (KPT * 32) + j * 32 + lane;
-            key[j] = idx < nValid ? s.keys[idx] : ~0ull;  // padding sorts last inside the tile and is never written
+            key[j] = idx < nValid ? s.keys[idx] : (KeyT)~(KeyT)0;  // padding sorts last inside the tile and is never written
         }
         // peers = lanes of the warp holding the same digit.  Two ways to get it, chosen per pass from the digit
         // histogram (CTA-uniform): MATCH.ANY iterates over the distinct values in the warp (measured per 4096-key
@@ -428,7 +431,7 @@ k_sort_onesweep(const unsigned long long* __restrict__ keysIn, const uint32_t* _
             const uint32_t i = k * kSortThreads + tid;
             if (i < nValid)
             {
-                const unsigned long long kk = s.keys[i];
+                const KeyT kk = s.keys[i];
                 const uint32_t g = s.globalBase[digit_of(kk, shift, mask)] + i;
                 keysOut[g] = kk;
                 valsOut[g] = s.vals[i];
@@ -436,10 +439,9 @@ k_sort_onesweep(const unsigned long long* __restrict__ keysIn, const uint32_t* _
                 {
                     // last pass: neighbouring slots with the same high word (tile id) are neighbours in the output too,
                     // so only the first / last slot of each tile-id group in this CTA's tile can be a range end point
-                    const uint32_t t = (uint32_t)(kk >> 32);
-                    const uint32_t* hiWords = reinterpret_cast<const uint32_t*>(s.keys) + 1;
-                    const uint32_t tp = i > 0 ? hiWords[2 * (i - 1)] : ~t;
-                    const uint32_t tn = i + 1 < nValid ? hiWords[2 * (i + 1)] : ~t;
+                    const uint32_t t = (uint32_t)(kk >> rangeShift);  // tile id: high word of a u64 key, a u32 key itself
+                    const uint32_t tp = i > 0 ? (uint32_t)(s.keys[i - 1] >> rangeShift) : ~t;
+                    const uint32_t tn = i + 1 < nValid ? (uint32_t)(s.keys[i + 1] >> rangeShift) : ~t;
                     if (t < numRangeTiles)
                     {
                         if (tp != t) atomicMax(&tileRanges[t].x, ~g);
@@ -464,24 +466,25 @@ size_t sort_status_bytes(uint64_t capacity, int passes)
     return (size_t)passes * maxTiles * kRadixSize * sizeof(unsigned long long);
 }
 
-template <int KPT>
-static cudaError_t launch_passes_t(unsigned long long* keysA, uint32_t* valsA, unsigned long long* keysB, uint32_t* valsB, const uint32_t* nDevice,
+template <int KPT, typename KeyT>
+static cudaError_t launch_passes_t(KeyT* keysA, uint32_t* valsA, KeyT* keysB, uint32_t* valsB, const uint32_t* nDevice,
                                    uint64_t capacity, int beginBit, int endBit, const SortWorkspace& ws, int numSMs, cudaStream_t stream)
 {
-    using Smem = SortSmem<KPT>;
+    using Smem = SortSmem<KPT, KeyT>;
+    constexpr int kRangeShift = sizeof(KeyT) == 8 ? 32 : 0;  // where the tile id sits in a key
     static bool attrSet[64] = {};
     int dev = 0;
     cudaGetDevice(&dev);
     if (!attrSet[dev & 63])
     {
-        cudaError_t e = cudaFuncSetAttribute(k_sort_onesweep<KPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem));
+        cudaError_t e = cudaFuncSetAttribute(k_sort_onesweep<KPT, KeyT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem));
         if (e != cudaSuccess) return e;
         attrSet[dev & 63] = true;
     }
     const int passes = (endBit - beginBit + kRadixBits - 1) / kRadixBits;
     const uint64_t maxTiles = (capacity + kSortMinTileKeys - 1) / kSortMinTileKeys + 1;
     const uint32_t capTiles = (uint32_t)((capacity + Smem::kTile - 1) / Smem::kTile);
-    const uint32_t ctasPerSM = KPT == 16 ? 3u : 5u;
+    const uint32_t ctasPerSM = KPT == 16 ? (sizeof(KeyT) == 4 ? 4u : 3u) : 5u;
     const uint32_t grid = max(1u, min((uint32_t)numSMs * ctasPerSM, capTiles));
     unsigned long long* dTl = nullptr;
     size_t tlWords = 0;
@@ -495,19 +498,19 @@ static cudaError_t launch_passes_t(unsigned long long* keysA, uint32_t* valsA, u
 #endif
     for (int p = 0; p < passes; p++)
     {
-        const unsigned long long* kin = (p & 1) ? keysB : keysA;
+        const KeyT* kin = (p & 1) ? keysB : keysA;
         const uint32_t* vin = (p & 1) ? valsB : valsA;
-        unsigned long long* kout = (p & 1) ? keysA : keysB;
+        KeyT* kout = (p & 1) ? keysA : keysB;
         uint32_t* vout = (p & 1) ? valsA : valsB;
         const int shift = beginBit + p * kRadixBits;
         const bool last = p == passes - 1;
         const int nshift = last ? 0 : shift + kRadixBits;
-        k_sort_onesweep<KPT><<<grid, kSortThreads, sizeof(Smem), stream>>>(
+        k_sort_onesweep<KPT, KeyT><<<grid, kSortThreads, sizeof(Smem), stream>>>(
             kin, vin, kout, vout, nDevice, shift, digit_mask(shift, endBit), nshift, last ? 0u : digit_mask(nshift, endBit),
             ws.histograms + (ws.passOffset + p) * kRadixSize, last ? nullptr : ws.histograms + (ws.passOffset + p + 1) * kRadixSize,
             ws.status + (size_t)(ws.passOffset + p) * maxTiles * kRadixSize, ws.tickets + ws.passOffset + p, ws.generation, dTl ? dTl + p * tlWords : nullptr,
-            last && shift >= 32 ? ws.tileRanges : nullptr, ws.numRangeTiles,  // the digit must be part of the tile id
-            (uint32_t)maxTiles);
+            last && shift >= kRangeShift ? ws.tileRanges : nullptr, ws.numRangeTiles,  // the digit must be part of the tile id
+            (uint32_t)maxTiles, kRangeShift);
     }
 #ifdef SPL_SORT_TIMELINE
     if (tlPath)
@@ -551,8 +554,17 @@ cudaError_t launch_sort_passes(unsigned long long* keysA, uint32_t* valsA, unsig
 {
     const int passes = (endBit - beginBit + kRadixBits - 1) / kRadixBits;
     if (passes < 1 || passes > kMaxSortPasses) return cudaErrorInvalidValue;
-    if (ws.keysPerThread == 8) return launch_passes_t<8>(keysA, valsA, keysB, valsB, nDevice, capacity, beginBit, endBit, ws, numSMs, stream);
-    return launch_passes_t<16>(keysA, valsA, keysB, valsB, nDevice, capacity, beginBit, endBit, ws, numSMs, stream);
+    if (ws.keysPerThread == 8) return launch_passes_t<8, unsigned long long>(keysA, valsA, keysB, valsB, nDevice, capacity, beginBit, endBit, ws, numSMs, stream);
+    return launch_passes_t<16, unsigned long long>(keysA, valsA, keysB, valsB, nDevice, capacity, beginBit, endBit, ws, numSMs, stream);
+}
+
+cudaError_t launch_sort_passes32(uint32_t* keysA, uint32_t* valsA, uint32_t* keysB, uint32_t* valsB, const uint32_t* nDevice, uint64_t capacity,
+                                 int beginBit, int endBit, const SortWorkspace& ws, int numSMs, cudaStream_t stream)
+{
+    const int passes = (endBit - beginBit + kRadixBits - 1) / kRadixBits;
+    if (passes < 1 || passes > 4 || endBit > 32) return cudaErrorInvalidValue;
+    if (ws.keysPerThread == 8) return launch_passes_t<8, uint32_t>(keysA, valsA, keysB, valsB, nDevice, capacity, beginBit, endBit, ws, numSMs, stream);
+    return launch_passes_t<16, uint32_t>(keysA, valsA, keysB, valsB, nDevice, capacity, beginBit, endBit, ws, numSMs, stream);
 }
 
 cudaError_t launch_radix_sort(unsigned long long* keysA, uint32_t* valsA, unsigned long long* keysB, uint32_t* valsB, const uint32_t* nDevice,

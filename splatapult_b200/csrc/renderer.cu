@@ -64,7 +64,8 @@ struct RendererImpl
     unsigned long long* dScan = nullptr;
     unsigned long long* dStatus = nullptr;
     uint32_t sortGeneration = 0;
-    const unsigned long long* dSortedKeys = nullptr;  // where the last LSD sort left its result
+    const unsigned long long* dSortedKeys = nullptr;  // where the last LSD sort left its result ...
+    int sortedKeyBytes = 8;                           // ... as u64 (tile << 32 | depthKey) or, default path, u32 tile ids
     const uint32_t* dSortedVals = nullptr;
     int sortKpt = 16;
     uint2* dRanges = nullptr;
@@ -339,30 +340,37 @@ struct RendererImpl
                 SortWorkspace ws{dHist, dStatus, dCtr->sortTickets, capacity, sortGeneration, sortKpt, 0, rangesFused ? dRanges : nullptr, numTiles};
                 CU_TRY(launch_sort_passes(dKeysA, dValsA, dKeysB, dValsB, &dCtr->usedInstances, capacity, 0, sortBits, ws, numSMs, stream));
                 launches += sortPasses;
+                sortedKeyBytes = 8;
                 dSortedKeys = (sortPasses & 1) ? dKeysB : dKeysA;
                 dSortedVals = (sortPasses & 1) ? dValsB : dValsA;
             }
             else
             {
                 // the four depth digits are common to all instances of a gaussian: those passes run on the N
-                // (depthKey, id) pairs BEFORE tile expansion; the expansion emits in depth order; only the tile digits
-                // are sorted on the D instances.  Same stable LSD sort of the same keys, half the element-passes.
+                // (u32 depthKey, id) pairs BEFORE tile expansion; the expansion emits (u32 tile id, id) in depth order; only
+                // the tile digits are sorted on the D instances, which do not carry the depth key (stable passes keep the
+                // depth order).  Same stable LSD sort of the same (tile | depth) order, half the element-passes at 8 instead
+                // of 12 bytes per element.  The u32 arrays live in the u64 key buffers.
                 const int tileBits = sortBits - kDepthBits, tilePasses = (tileBits + kRadixBits - 1) / kRadixBits;
-                CU_TRY(launch_project_keys(cloud, fc, dRec, dKeysA, dValsA, reinterpret_cast<uint2*>(dSide), dCtr, dHist, stream));
+                uint32_t* keysA32 = reinterpret_cast<uint32_t*>(dKeysA);
+                uint32_t* keysB32 = reinterpret_cast<uint32_t*>(dKeysB);
+                CU_TRY(launch_project_keys(cloud, fc, dRec, keysA32, dValsA, reinterpret_cast<uint2*>(dSide), dCtr, dHist, stream));
                 launches += n ? 1 : 0;
                 if (profile) CU_TRY(cudaEventRecord(ev[1], stream));
                 SortWorkspace wsDepth{dHist, dStatus, dCtr->sortTickets, capacity, sortGeneration, sortKpt, 0};
-                CU_TRY(launch_sort_passes(dKeysA, dValsA, dKeysB, dValsB, &dCtr->sortCount, capacity, 0, kDepthBits, wsDepth, numSMs, stream));
-                CU_TRY(launch_emit_sorted(dKeysA, dValsA, reinterpret_cast<const uint2*>(dSide), n, fc, dKeysB, dValsB, dCtr, dScan, (uint32_t)capacity,
+                CU_TRY(launch_sort_passes32(keysA32, dValsA, keysB32, dValsB, &dCtr->sortCount, capacity, 0, kDepthBits, wsDepth, numSMs, stream));
+                // 4 passes: the sorted ids are back in dValsA
+                CU_TRY(launch_emit_sorted(dValsA, reinterpret_cast<const uint2*>(dSide), n, fc, keysB32, dValsB, dCtr, dScan, (uint32_t)capacity,
                                           dHist + 4 * kRadixSize, stream));
                 launches += 4 + (n ? 1 : 0);
                 if (profile) CU_TRY(cudaEventRecord(ev[6], stream));
                 dSortedKeys = dKeysB;
                 dSortedVals = dValsB;
+                sortedKeyBytes = 4;
                 if (tilePasses > 0)
                 {
                     SortWorkspace wsTile{dHist, dStatus, dCtr->sortTickets, capacity, sortGeneration, sortKpt, 4, rangesFused ? dRanges : nullptr, numTiles};
-                    CU_TRY(launch_sort_passes(dKeysB, dValsB, dKeysA, dValsA, &dCtr->usedInstances, capacity, kDepthBits, sortBits, wsTile, numSMs, stream));
+                    CU_TRY(launch_sort_passes32(keysB32, dValsB, keysA32, dValsA, &dCtr->usedInstances, capacity, 0, tileBits, wsTile, numSMs, stream));
                     launches += tilePasses;
                     if (tilePasses & 1) { dSortedKeys = dKeysA; dSortedVals = dValsA; }
                 }
@@ -370,7 +378,7 @@ struct RendererImpl
             if (profile) CU_TRY(cudaEventRecord(ev[2], stream));
             if (!rangesFused)
             {
-                CU_TRY(launch_tile_ranges(dSortedKeys, &dCtr->usedInstances, capacity, dRanges, numTiles, numSMs, stream));
+                CU_TRY(launch_tile_ranges(dSortedKeys, sortedKeyBytes, &dCtr->usedInstances, capacity, dRanges, numTiles, numSMs, stream));
                 launches += 1;
             }
             if (profile) CU_TRY(cudaEventRecord(ev[3], stream));
@@ -584,6 +592,21 @@ struct RendererImpl
                     if (what == SPL_TAP_KEYS) static_cast<unsigned long long*>(host)[k] = ((unsigned long long)t << 32) | (pairs[k] >> 32);
                     else static_cast<uint32_t*>(host)[k] = (uint32_t)pairs[k];
                 }
+            return ok();
+        }
+        if (what == SPL_TAP_KEYS && sortedKeyBytes == 4)
+        {
+            // default path: the instances carry bare tile ids; the tap shows the (tile << 32 | depthKey) stream they stand for
+            const size_t d = c.usedInstances;
+            if (bytes < d * 8) return fail(SPL_ERR_ARG, "tap buffer too small");
+            std::vector<uint32_t> tiles(d), ids(d);
+            std::vector<ProjRecord> recs(n);
+            if (d) CU_TRY(cudaMemcpyAsync(tiles.data(), sortedKeys(), d * 4, cudaMemcpyDeviceToHost, stream));
+            if (d) CU_TRY(cudaMemcpyAsync(ids.data(), sortedVals(), d * 4, cudaMemcpyDeviceToHost, stream));
+            if (n) CU_TRY(cudaMemcpyAsync(recs.data(), dRec, (size_t)n * sizeof(ProjRecord), cudaMemcpyDeviceToHost, stream));
+            CU_TRY(cudaStreamSynchronize(stream));
+            for (size_t k = 0; k < d; k++)
+                static_cast<unsigned long long*>(host)[k] = ((unsigned long long)tiles[k] << 32) | (ids[k] < n ? recs[ids[k]].key : 0u);
             return ok();
         }
         switch (what)
