@@ -59,7 +59,7 @@ __device__ __forceinline__ float srgb_to_linear(float s)
 
 // splat_vert.glsl:51-127; sh planes hold vec4 blocks {r,g,b}_sh{0..3}
 template <int SH_MODE>
-__device__ __forceinline__ void radiance(const PackedCloud& cloud, uint32_t i, float vx, float vy, float vz, float* rgb, const float* dcPre)
+__device__ __forceinline__ void radiance(float vx, float vy, float vz, float* rgb, const float* dcPre, const float4* shPre)
 {
     float b[16];
     const float vx2 = vx * vx, vy2 = vy * vy, vz2 = vz * vz;
@@ -97,7 +97,7 @@ __device__ __forceinline__ void radiance(const PackedCloud& cloud, uint32_t i, f
         }
         else if (SH_MODE == 1)
         {
-            const float4 s0 = __ldg(cloud.sh[c] + i);
+            const float4 s0 = shPre[c];
             acc = b[0] * s0.x;
             acc = acc + b[1] * s0.y;
             acc = acc + b[2] * s0.z;
@@ -105,7 +105,7 @@ __device__ __forceinline__ void radiance(const PackedCloud& cloud, uint32_t i, f
         }
         else
         {
-            float4 s = __ldg(cloud.sh[4 * c] + i);
+            float4 s = shPre[4 * c];
             acc = b[0] * s.x;
             acc = acc + b[1] * s.y;
             acc = acc + b[2] * s.z;
@@ -113,7 +113,7 @@ __device__ __forceinline__ void radiance(const PackedCloud& cloud, uint32_t i, f
 #pragma unroll
             for (int j = 1; j < 4; j++)
             {
-                s = __ldg(cloud.sh[4 * c + j] + i);
+                s = shPre[4 * c + j];
                 acc = acc + b[4 * j + 0] * s.x;
                 acc = acc + b[4 * j + 1] * s.y;
                 acc = acc + b[4 * j + 2] * s.z;
@@ -155,6 +155,18 @@ __device__ __forceinline__ Projected project_gaussian(const PackedCloud& cloud, 
         {
 #pragma unroll
             for (int c = 0; c < 3; c++) dcPre[c] = __ldg(cloud.dc[c] + i);
+        }
+        // same for the SH planes (48 / 192 bytes per gaussian): all loads of a gaussian are in flight together instead
+        // of one dependent round trip after the other (volatile asm: the compiler would otherwise sink them to their uses)
+        constexpr int kShPlanes = SH_MODE == 3 ? 12 : (SH_MODE == 1 ? 3 : 1);
+        float4 shPre[kShPlanes];
+        if (SH_MODE != 0)
+        {
+#pragma unroll
+            for (int k = 0; k < kShPlanes; k++)
+                asm volatile("ld.global.nc.v4.f32 {%0,%1,%2,%3}, [%4];"
+                             : "=f"(shPre[k].x), "=f"(shPre[k].y), "=f"(shPre[k].z), "=f"(shPre[k].w)
+                             : "l"(cloud.sh[k] + i));
         }
 
         // ---- K1 presort_compute.glsl:42-56
@@ -215,7 +227,7 @@ __device__ __forceinline__ Projected project_gaussian(const PackedCloud& cloud, 
                 const float dx = x - fc.eye[0], dy = y - fc.eye[1], dz = z - fc.eye[2];
                 const float len = sqrtf((dx * dx + dy * dy) + dz * dz);
                 float rgb[3];
-                radiance<SH_MODE>(cloud, i, dx / len, dy / len, dz / len, rgb, dcPre);
+                radiance<SH_MODE>(dx / len, dy / len, dz / len, rgb, dcPre, shPre);
                 if (fc.srgb)
                 {
 #pragma unroll
@@ -340,7 +352,17 @@ k_project(const PackedCloud cloud, const __grid_constant__ FrameConstants fc, Pr
             if (vbid == gridDim.x - 1) ctr->totalInstances = excl + blockTotal;
         }
     }
-    if (lane == 0 && nVisibleWarp) atomicAdd(&ctr->visible, nVisibleWarp);
+    __syncthreads();
+    // frame counters: one atomic per CTA (same-address atomics serialise in L2), through sWarpTotal, which is free now
+    if (lane == 0) sWarpTotal[warp] = nVisibleWarp;
+    __syncthreads();
+    if (tid == 0)
+    {
+        uint32_t vis = 0;
+#pragma unroll
+        for (int w = 0; w < kProjThreads / 32; w++) vis += sWarpTotal[w];
+        if (vis) atomicAdd(&ctr->visible, vis);
+    }
     __syncthreads();
 
     // ---- warp-cooperative, coalesced key emission
@@ -365,7 +387,7 @@ k_project(const PackedCloud cloud, const __grid_constant__ FrameConstants fc, Pr
     uint32_t usedEnd = cntE ? gOff + cntE : 0u;
 #pragma unroll
     for (int d = 16; d; d >>= 1) usedEnd = max(usedEnd, __shfl_xor_sync(0xffffffffu, usedEnd, d));
-    if (lane == 0 && usedEnd) atomicMax(&ctr->usedInstances, usedEnd);
+    if (lane == 0) sWarpTotal[warp] = usedEnd;
 
     const uint32_t tilesX = (uint32_t)fc.tilesX;
     for (uint32_t j0 = 0; j0 < T; j0 += 32)
@@ -394,9 +416,16 @@ k_project(const PackedCloud cloud, const __grid_constant__ FrameConstants fc, Pr
             vals[oOff + k] = oId;
         }
     }
+    __syncthreads();
+    if (tid == 0)
+    {
+        uint32_t m = 0;
+#pragma unroll
+        for (int w = 0; w < kProjThreads / 32; w++) m = max(m, sWarpTotal[w]);
+        if (m) atomicMax(&ctr->usedInstances, m);
+    }
     if (digit0Hist)
     {
-        __syncthreads();
         const uint32_t c = sDigit0[tid];
         if (c) atomicAdd(digit0Hist + tid, c);
     }
@@ -562,10 +591,18 @@ k_emit_sorted(const uint32_t* __restrict__ sortedVals, const uint2* __restrict__
     }
 #pragma unroll
     for (int d = 16; d; d >>= 1) usedEnd = max(usedEnd, __shfl_xor_sync(0xffffffffu, usedEnd, d));
-    if (lane == 0 && usedEnd) atomicMax(&ctr->usedInstances, usedEnd);
+    // one atomic per CTA on the frame counter, not one per warp: same-address atomics serialise in L2
+    if (lane == 0) sWarpTotal[0][warp] = usedEnd;  // sWarpTotal is free again: every warp passed the barrier after the scan
+    __syncthreads();
+    if (tid == 0)
+    {
+        uint32_t m = 0;
+#pragma unroll
+        for (int w = 0; w < kWarps; w++) m = max(m, sWarpTotal[0][w]);
+        if (m) atomicMax(&ctr->usedInstances, m);
+    }
     if (tileDigitHist)
     {
-        __syncthreads();
         const uint32_t c = sDigit0[tid];
         if (c) atomicAdd(tileDigitHist + tid, c);
     }
@@ -582,25 +619,40 @@ k_project_keys(const PackedCloud cloud, const __grid_constant__ FrameConstants f
                uint32_t* __restrict__ keys, uint32_t* __restrict__ vals, uint2* __restrict__ side, FrameCounters* __restrict__ ctr,
                uint32_t* __restrict__ digit0Hist)
 {
+    // grid-stride over chunks of 256 gaussians: the CTA keeps its digit histogram and its visible count across chunks
+    // and flushes them once.  (With one CTA per chunk and one atomicAdd per warp on ctr->visible, that single L2
+    // address took N/32 serialised atomics: the kernel's time was their time -- 58 us at 1 M, 553 us at 6 M gaussians.)
     __shared__ uint32_t sDigit0[kRadixSize];
-    const int tid = threadIdx.x, lane = tid & 31;
+    const int tid = threadIdx.x;
     sDigit0[tid] = 0;
     __syncthreads();
-    const uint32_t i = blockIdx.x * kProjThreads + tid;
-    const bool inRange = i < cloud.n;
-    const Projected pg = project_gaussian<SH_MODE>(cloud, fc, rec, i, inRange);
-    if (inRange)
+    uint32_t visibleMine = 0;
+    const uint32_t numChunks = (cloud.n + kProjThreads - 1) / kProjThreads;
+    for (uint32_t chunk = blockIdx.x; chunk < numChunks; chunk += gridDim.x)
     {
-        const uint32_t key = pg.count ? pg.refKey : 0xFFFFFFFFu;
-        keys[i] = key;
-        vals[i] = i;
-        side[i] = pg.count ? make_uint2(pg.x0 | (pg.y0 << 16), pg.w | (pg.h << 16)) : make_uint2(0u, 0u);
-        smem_red_add(&sDigit0[key & (kRadixSize - 1)], 1u);
+        const uint32_t i = chunk * kProjThreads + tid;
+        const bool inRange = i < cloud.n;
+        const Projected pg = project_gaussian<SH_MODE>(cloud, fc, rec, i, inRange);
+        if (inRange)
+        {
+            const uint32_t key = pg.count ? pg.refKey : 0xFFFFFFFFu;
+            keys[i] = key;
+            vals[i] = i;
+            side[i] = pg.count ? make_uint2(pg.x0 | (pg.y0 << 16), pg.w | (pg.h << 16)) : make_uint2(0u, 0u);
+            smem_red_add(&sDigit0[key & (kRadixSize - 1)], 1u);
+        }
+        visibleMine += pg.visible ? 1u : 0u;
     }
-    const uint32_t nVisibleWarp = __popc(__ballot_sync(0xffffffffu, pg.visible));
-    if (lane == 0 && nVisibleWarp) atomicAdd(&ctr->visible, nVisibleWarp);
     if (blockIdx.x == 0 && tid == 0) ctr->sortCount = cloud.n;
+    // CTA total of the visible counts: warp reduce, then one atomic per warp into shared memory, one global atomic
+    __shared__ uint32_t sVisible;
+    if (tid == 0) sVisible = 0;
+    __syncthreads();  // also: every thread's histogram updates are done
+#pragma unroll
+    for (int d = 16; d; d >>= 1) visibleMine += __shfl_xor_sync(0xffffffffu, visibleMine, d);
+    if ((tid & 31) == 0 && visibleMine) atomicAdd(&sVisible, visibleMine);
     __syncthreads();
+    if (tid == 0 && sVisible) atomicAdd(&ctr->visible, sVisible);
     const uint32_t c = sDigit0[tid];
     if (c) atomicAdd(digit0Hist + tid, c);
 }
@@ -749,8 +801,17 @@ cudaError_t launch_project(const PackedCloud& cloud, const FrameConstants& fc, P
 cudaError_t launch_project_keys(const PackedCloud& cloud, const FrameConstants& fc, ProjRecord* rec, uint32_t* keys, uint32_t* vals,
                                 uint2* side, FrameCounters* ctr, uint32_t* digit0Hist, cudaStream_t stream)
 {
-    const uint32_t blocks = project_num_blocks(cloud.n);
+    uint32_t blocks = project_num_blocks(cloud.n);
     if (blocks == 0) return cudaSuccess;
+    static int numSMs = 0;
+    if (!numSMs)
+    {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&numSMs, cudaDevAttrMultiProcessorCount, dev);
+        if (numSMs <= 0) numSMs = 148;
+    }
+    blocks = min(blocks, (uint32_t)numSMs * 8u);  // persistent, grid-stride: 8 CTAs of 256 threads per SM
     switch (cloud.shMode)
     {
     case 0: k_project_keys<0><<<blocks, kProjThreads, 0, stream>>>(cloud, fc, rec, keys, vals, side, ctr, digit0Hist); break;
