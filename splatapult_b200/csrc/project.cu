@@ -16,6 +16,8 @@
 // order, divisions and square roots are IEEE (nvcc defaults -prec-div/-prec-sqrt=true, -ftz=false), so the
 // projected records equal oracle/splat_oracle.c:project_one() bit for bit.  The kernel is HBM-bound; the
 // extra unfused flops are free.
+#include <cstdlib>
+
 #include "device_common.cuh"
 #include "kernels.h"
 
@@ -803,15 +805,25 @@ cudaError_t launch_project_keys(const PackedCloud& cloud, const FrameConstants& 
 {
     uint32_t blocks = project_num_blocks(cloud.n);
     if (blocks == 0) return cudaSuccess;
-    static int numSMs = 0;
-    if (!numSMs)
+    // persistent, grid-stride: as many CTAs as are resident at once (a multiple of the SM count), times `waves`
+    // (SPL_PROJECT_WAVES overrides, for tuning)
+    static int ctasPerWave[4] = {0, 0, 0, 0};
+    const int mode = cloud.shMode == 0 ? 0 : (cloud.shMode == 1 ? 1 : 3);
+    if (!ctasPerWave[mode])
     {
-        int dev = 0;
+        int dev = 0, numSMs = 0, occ = 0;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&numSMs, cudaDevAttrMultiProcessorCount, dev);
-        if (numSMs <= 0) numSMs = 148;
+        if (mode == 0) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_project_keys<0>, kProjThreads, 0);
+        else if (mode == 1) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_project_keys<1>, kProjThreads, 0);
+        else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_project_keys<3>, kProjThreads, 0);
+        ctasPerWave[mode] = (numSMs > 0 ? numSMs : 148) * (occ > 0 ? occ : 4);
     }
-    blocks = min(blocks, (uint32_t)numSMs * 8u);  // persistent, grid-stride: 8 CTAs of 256 threads per SM
+    // measured: one wave is best for the light kernels (34 us vs 40 / 43 us with 2 / 4 waves at 1 M gaussians, deg 0); the
+    // degree-3 kernel (89 registers, 2 CTAs per SM) balances its tail better with 4 (302 vs 311 us at 6 M)
+    static const int wavesEnv = getenv("SPL_PROJECT_WAVES") ? atoi(getenv("SPL_PROJECT_WAVES")) : 0;
+    const int waves = wavesEnv > 0 ? wavesEnv : (mode == 3 ? 4 : 1);
+    blocks = min(blocks, (uint32_t)(ctasPerWave[mode] * waves));
     switch (cloud.shMode)
     {
     case 0: k_project_keys<0><<<blocks, kProjThreads, 0, stream>>>(cloud, fc, rec, keys, vals, side, ctr, digit0Hist); break;
