@@ -685,10 +685,26 @@ k_project_bin(const PackedCloud cloud, const __grid_constant__ FrameConstants fc
     }
     const uint32_t wex = incl - pg.count;
     const uint32_t T = __shfl_sync(0xffffffffu, incl, 31);
+    // frame counters: one pair of atomics per CTA, not per warp (same-address atomics serialise in L2)
+    __shared__ uint32_t sVis[kProjThreads / 32], sTot[kProjThreads / 32];
     if (lane == 0)
     {
-        if (nVisibleWarp) atomicAdd(&ctr->visible, nVisibleWarp);
-        if (T) atomicAdd(&ctr->totalInstances, (unsigned long long)T);
+        sVis[threadIdx.x >> 5] = nVisibleWarp;
+        sTot[threadIdx.x >> 5] = T;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0)
+    {
+        uint32_t vis = 0;
+        unsigned long long tot = 0;
+#pragma unroll
+        for (int w = 0; w < kProjThreads / 32; w++)
+        {
+            vis += sVis[w];
+            tot += sTot[w];
+        }
+        if (vis) atomicAdd(&ctr->visible, vis);
+        if (tot) atomicAdd(&ctr->totalInstances, tot);
     }
     const uint32_t rectXY = pg.x0 | (pg.y0 << 16);
     const uint32_t tilesX = (uint32_t)fc.tilesX;
