@@ -13,7 +13,7 @@ struct Camera
     splat::vec2 fov;
 };
 
-class CamerasConfig
+class SPLAT_CPP_API CamerasConfig
 {
 public:
     CamerasConfig() = default;

@@ -11,7 +11,7 @@
 #include "binaryattribute.h"
 #include "splatmath.h"
 
-class GaussianCloud
+class SPLAT_CPP_API GaussianCloud
 {
 public:
     struct Options

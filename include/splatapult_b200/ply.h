@@ -9,8 +9,9 @@
 #include <vector>
 
 #include "binaryattribute.h"
+#include "splatmath.h"  // SPLAT_CPP_API
 
-class Ply
+class SPLAT_CPP_API Ply
 {
 public:
     Ply() = default;

@@ -13,6 +13,14 @@
 #include <cmath>
 #include <cstring>
 
+// the C++ drop-in classes (GaussianCloud, SplatRenderer, CamerasConfig, Ply) are exported from libsplat_b200.so next to
+// the C ABI; everything else in the library has hidden visibility
+#if defined(_WIN32)
+#define SPLAT_CPP_API
+#else
+#define SPLAT_CPP_API __attribute__((visibility("default")))
+#endif
+
 namespace splat
 {
 

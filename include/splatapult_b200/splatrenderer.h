@@ -17,7 +17,7 @@ struct spl_stats;
 
 namespace splat { struct RendererImpl; }
 
-class SplatRenderer
+class SPLAT_CPP_API SplatRenderer
 {
 public:
     enum class FrameBuffer { Float = 0 /* --fp32, GL_RGBA32F */, HalfFloat = 1 /* --fp16, GL_RGBA16F */ };

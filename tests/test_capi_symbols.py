@@ -36,6 +36,12 @@ def test_only_the_c_abi_is_exported(splat):
     names = [l.split()[-1] for l in out.splitlines() if " T " in l]
     c_names = [n for n in names if not n.startswith("_Z")]
     assert c_names and all(n.startswith("spl_") for n in c_names), c_names
+    # C++ symbols: exactly the four drop-in classes of include/splatapult_b200/*.h, none of the internals (namespace splat)
+    dem = subprocess.run(["nm", "-DC", "--defined-only", splat.library_path()], capture_output=True, text=True).stdout
+    cpp = [l.split(" T ", 1)[1] for l in dem.splitlines() if " T " in l and not l.split(" T ", 1)[1].startswith("spl_")]
+    classes = {n.split("::")[0] for n in cpp}
+    assert classes == {"GaussianCloud", "SplatRenderer", "CamerasConfig", "Ply"}, classes
+    assert not any(n.startswith("splat::") for n in cpp)
 
 
 def test_version_and_error_channel(splat):
