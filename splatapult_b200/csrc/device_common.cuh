@@ -24,12 +24,7 @@ constexpr int kSortMinTileKeys = kSortThreads * 8;                // smallest ti
 // generation per sort and zeroes the array whenever (generation & mask) wraps to 0 (every 31 sorts)
 constexpr uint32_t kSortGenerationMask = 31;
 
-// look-back status word: [31:30] flag, [29:0] count
-constexpr uint32_t kFlagAggregate = 1u << 30;
-constexpr uint32_t kFlagPrefix = 2u << 30;
-constexpr uint32_t kFlagMask = 3u << 30;
-constexpr uint32_t kValueMask = ~kFlagMask;
-constexpr uint64_t kMaxInstances = (1ull << 30) - 1;
+constexpr uint64_t kMaxInstances = (1ull << 30) - 1;  // tile instances one frame may hold
 
 // per-tile segment sort (binsort.cu): segments up to kSegSortSmallCap are sorted by a 256-thread CTA in 2 x 16 KiB
 // of static shared memory, up to kSegSortLargeCap by a 1024-thread CTA in 2 x 96 KiB, longer ones through global memory
