@@ -7,15 +7,20 @@
 //                                          screen centre, SH radiance (:51-127)
 //   K6 shader/splat_geom.glsl:22-54        2x2 inverse, guard-band cull.  The 3.5-sigma quad (:56-104) becomes
 //                                          a conservative tile rectangle.
-// and emits one u64 key (tile << 32 | depthKey) + u32 gaussian id per touched 16x16 tile.  Key slots are
-// assigned by a single-pass decoupled look-back scan over the per-gaussian tile counts, so emission order is
-// the gaussian index order (deterministic; the reference's compaction order is not) and the
-// instance count D never leaves the device.
+// Three consumers of the same per-gaussian function project_gaussian():
+//   k_project_keys (default path)  one (u32 depthKey, id) pair + tile rectangle per gaussian; after the depth digits
+//                                  are sorted on the gaussians, k_emit_sorted expands the sorted list into
+//                                  (u32 tile id, id) instances in depth order (scan + look-back + coalesced emission)
+//   k_project      (flat path)     projection + scan + emission of (tile << 32 | depthKey, id) in gaussian order
+//   k_project_bin  (binned path)   side records + per-tile instance counts
+// Key slots come from a single-pass decoupled look-back scan over the tile counts, so the emission order is
+// deterministic (the reference's compaction order is not) and the instance count D never leaves the device.
 //
 // This translation unit is compiled with -fmad=false: every a*b+c below is two IEEE roundings in source
 // order, divisions and square roots are IEEE (nvcc defaults -prec-div/-prec-sqrt=true, -ftz=false), so the
-// projected records equal oracle/splat_oracle.c:project_one() bit for bit.  The kernel is HBM-bound; the
-// extra unfused flops are free.
+// projected records equal oracle/splat_oracle.c:project_one() bit for bit.
+// Frame counters (visible, usedInstances, ...) take ONE atomic per CTA: a per-warp atomicAdd on one L2 address was,
+// at N/32 serialised operations, the whole run time of the projection kernel until it was found.
 #include <cstdlib>
 
 #include "device_common.cuh"
