@@ -30,6 +30,27 @@ int set_error(int code, const std::string& msg)
     g_lastError = msg;
     return code;
 }
+// no C++ exception crosses the C ABI: allocation failures and anything else a host-side call throws become status codes
+template <typename F>
+int guarded(F&& f) noexcept
+{
+    try
+    {
+        return f();
+    }
+    catch (const std::bad_alloc&)
+    {
+        return set_error(SPL_ERR_ALLOC, "out of host memory");
+    }
+    catch (const std::exception& e)
+    {
+        return set_error(SPL_ERR_ARG, std::string("C++ exception: ") + e.what());
+    }
+    catch (...)
+    {
+        return set_error(SPL_ERR_ARG, "unknown C++ exception");
+    }
+}
 int from_renderer(spl_renderer* h, bool okFlag)
 {
     if (okFlag) return SPL_OK;
@@ -62,40 +83,52 @@ void spl_cloud_destroy(spl_cloud* c) { delete c; }
 
 int spl_cloud_import_ply(spl_cloud* c, const char* path)
 {
+    return guarded([&]() -> int {
     if (!c || !path) return set_error(SPL_ERR_ARG, "null argument");
     if (!c->gc->ImportPly(path)) return set_error(SPL_ERR_IO, c->gc->GetError());
     return SPL_OK;
+    });
 }
 int spl_cloud_import_ply_gpu(spl_cloud* c, const char* path, int device)
 {
+    return guarded([&]() -> int {
     if (!c || !path) return set_error(SPL_ERR_ARG, "null argument");
     if (spl_device_count() < 1) return set_error(SPL_ERR_CUDA, "no CUDA device: spl_cloud_import_ply_gpu has no CPU fallback (use spl_cloud_import_ply)");
     if (!c->gc->ImportPlyGpu(path, device)) return set_error(SPL_ERR_IO, c->gc->GetError());
     return SPL_OK;
+    });
 }
 int spl_cloud_export_ply(const spl_cloud* c, const char* path)
 {
+    return guarded([&]() -> int {
     if (!c || !path) return set_error(SPL_ERR_ARG, "null argument");
     if (!c->gc->ExportPly(path)) return set_error(SPL_ERR_IO, c->gc->GetError());
     return SPL_OK;
+    });
 }
 int spl_cloud_init_debug_cloud(spl_cloud* c)
 {
+    return guarded([&]() -> int {
     if (!c) return set_error(SPL_ERR_ARG, "null argument");
     c->gc->InitDebugCloud();
     return SPL_OK;
+    });
 }
 int spl_cloud_prune_splats(spl_cloud* c, const float origin[3], uint32_t count)
 {
+    return guarded([&]() -> int {
     if (!c || !origin) return set_error(SPL_ERR_ARG, "null argument");
     c->gc->PruneSplats(splat::vec3{origin[0], origin[1], origin[2]}, count);
     return SPL_OK;
+    });
 }
 int spl_cloud_set_raw(spl_cloud* c, const void* aos, size_t n, size_t stride, int has_full_sh)
 {
+    return guarded([&]() -> int {
     if (!c || (!aos && n)) return set_error(SPL_ERR_ARG, "null argument");
     if (!c->gc->SetRawData(aos, n, stride, has_full_sh != 0)) return set_error(SPL_ERR_ARG, c->gc->GetError());
     return SPL_OK;
+    });
 }
 size_t spl_cloud_num_gaussians(const spl_cloud* c) { return c ? c->gc->GetNumGaussians() : 0; }
 size_t spl_cloud_stride(const spl_cloud* c) { return c ? c->gc->GetStride() : 0; }
@@ -130,30 +163,40 @@ int spl_renderer_configure(spl_renderer* h, int device, int fb_format, void* cud
 }
 int spl_renderer_init(spl_renderer* h, const spl_cloud* c, int srgb, int use_rgc)
 {
+    return guarded([&]() -> int {
     if (!h || !c) return set_error(SPL_ERR_ARG, "null argument");
     return from_renderer(h, h->r.Init(c->gc, srgb != 0, use_rgc != 0));
+    });
 }
 int spl_renderer_init_device_aos(spl_renderer* h, const void* device_aos, size_t n, size_t stride, int has_full_sh, int srgb)
 {
+    return guarded([&]() -> int {
     if (!h || (!device_aos && n)) return set_error(SPL_ERR_ARG, "null argument");
     return from_renderer(h, h->r.InitFromDevice(device_aos, n, stride, has_full_sh != 0, srgb != 0));
+    });
 }
 int spl_renderer_init_ply(spl_renderer* h, const char* path, int import_full_sh, int srgb)
 {
+    return guarded([&]() -> int {
     if (!h || !path) return set_error(SPL_ERR_ARG, "null argument");
     return from_renderer(h, h->r.InitFromPly(path, import_full_sh != 0, srgb != 0));
+    });
 }
 int spl_renderer_sort(spl_renderer* h, const float cam[16], const float proj[16], const float vp[4], const float nf[2])
 {
+    return guarded([&]() -> int {
     if (!h || !cam || !proj || !vp || !nf) return set_error(SPL_ERR_ARG, "null argument");
     h->r.Sort(splat::mat4::from(cam), splat::mat4::from(proj), splat::vec4{vp[0], vp[1], vp[2], vp[3]}, splat::vec2{nf[0], nf[1]});
     return from_renderer(h, h->r.LastStatus() == 0);
+    });
 }
 int spl_renderer_render(spl_renderer* h, const float cam[16], const float proj[16], const float vp[4], const float nf[2])
 {
+    return guarded([&]() -> int {
     if (!h || !cam || !proj || !vp || !nf) return set_error(SPL_ERR_ARG, "null argument");
     h->r.Render(splat::mat4::from(cam), splat::mat4::from(proj), splat::vec4{vp[0], vp[1], vp[2], vp[3]}, splat::vec2{nf[0], nf[1]});
     return from_renderer(h, h->r.LastStatus() == 0);
+    });
 }
 int spl_renderer_framebuffer(spl_renderer* h, void** device_ptr, int* w, int* hgt, size_t* pitch, int* fmt)
 {
@@ -170,8 +213,10 @@ int spl_renderer_read_framebuffer_async(spl_renderer* h, void* host, size_t byte
 }
 int spl_renderer_read_framebuffer(spl_renderer* h, void* host, size_t bytes)
 {
+    return guarded([&]() -> int {
     if (!h || !host) return set_error(SPL_ERR_ARG, "null argument");
     return from_renderer(h, h->r.ReadFramebuffer(host, bytes));
+    });
 }
 int spl_renderer_read_rgba8_async(spl_renderer* h, void* host, size_t bytes)
 {
@@ -180,8 +225,10 @@ int spl_renderer_read_rgba8_async(spl_renderer* h, void* host, size_t bytes)
 }
 int spl_renderer_read_rgba8(spl_renderer* h, void* host, size_t bytes)
 {
+    return guarded([&]() -> int {
     if (!h || !host) return set_error(SPL_ERR_ARG, "null argument");
     return from_renderer(h, h->r.ReadPresented8(host, bytes));
+    });
 }
 int spl_renderer_fence_copies(spl_renderer* h)
 {
@@ -205,8 +252,10 @@ int spl_renderer_stats(spl_renderer* h, spl_stats* out)
 }
 int spl_renderer_reserve(spl_renderer* h, uint64_t cap)
 {
+    return guarded([&]() -> int {
     if (!h) return set_error(SPL_ERR_ARG, "null argument");
     return from_renderer(h, h->r.Reserve(cap));
+    });
 }
 int spl_renderer_set_option(spl_renderer* h, int option, double value)
 {
@@ -215,8 +264,10 @@ int spl_renderer_set_option(spl_renderer* h, int option, double value)
 }
 int spl_renderer_tap(spl_renderer* h, int what, void* host, size_t bytes)
 {
+    return guarded([&]() -> int {
     if (!h || !host) return set_error(SPL_ERR_ARG, "null argument");
     return from_renderer(h, h->r.Tap(what, host, bytes));
+    });
 }
 
 }  // extern "C"
@@ -232,9 +283,11 @@ spl_cameras* spl_cameras_create(void) { return new (std::nothrow) spl_cameras; }
 void spl_cameras_destroy(spl_cameras* c) { delete c; }
 int spl_cameras_import_json(spl_cameras* c, const char* path)
 {
+    return guarded([&]() -> int {
     if (!c || !path) return set_error(SPL_ERR_ARG, "null argument");
     if (!c->cfg.ImportJson(path)) return set_error(SPL_ERR_IO, c->cfg.GetError());
     return SPL_OK;
+    });
 }
 size_t spl_cameras_count(const spl_cameras* c) { return c ? c->cfg.GetNumCameras() : 0; }
 int spl_cameras_get(const spl_cameras* c, size_t index, float camera_mat[16], float fov[2])
@@ -346,6 +399,7 @@ int spl_sorter_sort(spl_sorter* s, void* d_keys_in, void* d_vals_in, void* d_key
 
 int spl_sort_pairs_host(const uint64_t* keys, const uint32_t* vals, uint64_t n, int begin_bit, int end_bit, uint64_t* keys_out, uint32_t* vals_out)
 {
+    return guarded([&]() -> int {
     if ((!keys || !vals || !keys_out || !vals_out) && n) return set_error(SPL_ERR_ARG, "null argument");
     if (n == 0) return SPL_OK;
     spl_sorter* s = spl_sorter_create(0, n);
@@ -374,10 +428,12 @@ int spl_sort_pairs_host(const uint64_t* keys, const uint32_t* vals, uint64_t n, 
     cudaFree(dk0); cudaFree(dk1); cudaFree(dv0); cudaFree(dv1);
     spl_sorter_destroy(s);
     return rc;
+    });
 }
 
 int spl_write_ppm(const char* path, const void* host_fb, int width, int height, int fb_format)
 {
+    return guarded([&]() -> int {
     if (!path || !host_fb || width <= 0 || height <= 0) return set_error(SPL_ERR_ARG, "bad argument");
     FILE* f = std::fopen(path, "wb");
     if (!f) return set_error(SPL_ERR_IO, std::string("failed to open ") + path);
@@ -405,6 +461,7 @@ int spl_write_ppm(const char* path, const void* host_fb, int width, int height, 
     }
     std::fclose(f);
     return SPL_OK;
+    });
 }
 
 void* spl_host_alloc(size_t bytes)

@@ -190,7 +190,16 @@ bool GaussianCloud::ImportPly(const std::string& plyFilename)
     auto readf = [](const BinaryAttribute& a, const void* v) { return a.type == BinaryAttribute::Type::Float ? a.Read<float>(v) : 0.0f; };
 
     InitAttribs();
-    Allocate(ply.GetVertexCount(), (hasFullSH ? kFullFloats : kBaseFloats) * sizeof(float));
+    try
+    {
+        Allocate(ply.GetVertexCount(), (hasFullSH ? kFullFloats : kBaseFloats) * sizeof(float));
+    }
+    catch (const std::exception&)
+    {
+        error = "cannot allocate " + std::to_string(ply.GetVertexCount()) + " gaussians";
+        numGaussians = 0;
+        return false;
+    }
     const size_t recFloats = gaussianSize / sizeof(float);
     float* rec = static_cast<float*>(data.get());
     const uint8_t* v = ply.GetData();
@@ -229,7 +238,16 @@ bool GaussianCloud::ImportPlyGpu(const std::string& plyFilename, int device)
     splat::make_ply_decode_layout(ply, opt.importFullSH, &layout, &fullSH);
     hasFullSH = fullSH;
     InitAttribs();
-    Allocate(ply.GetVertexCount(), (hasFullSH ? kFullFloats : kBaseFloats) * sizeof(float));
+    try
+    {
+        Allocate(ply.GetVertexCount(), (hasFullSH ? kFullFloats : kBaseFloats) * sizeof(float));
+    }
+    catch (const std::exception&)
+    {
+        error = "cannot allocate " + std::to_string(ply.GetVertexCount()) + " gaussians";
+        numGaussians = 0;
+        return false;
+    }
     std::string err;
     if (!splat::decode_ply_on_device(ply.GetData(), numGaussians, ply.GetVertexSize(), layout, hasFullSH, device, nullptr,
                                      static_cast<float*>(data.get()), nullptr, &err))

@@ -6,6 +6,7 @@
 #include "splatapult_b200/ply.h"
 
 #include <algorithm>
+#include <exception>
 #include <istream>
 #include <ostream>
 #include <sstream>
@@ -85,7 +86,25 @@ bool Ply::Parse(std::istream& in)
     vertexCount = vertexSize = 0;
     error.clear();
     if (!ParseHeader(in)) return false;
-    AllocData(vertexCount);
+    // a header may claim any vertex count: the reference's `new uint8_t[size * count]` (ply.cpp:83) would throw out
+    // of the application; a library reports it
+    if (vertexSize && vertexCount > static_cast<size_t>(-1) / vertexSize)
+    {
+        error = "vertex count overflows the address space";
+        vertexCount = 0;
+        return false;
+    }
+    try
+    {
+        AllocData(vertexCount);
+    }
+    catch (const std::exception&)
+    {
+        error = "cannot allocate " + std::to_string(vertexCount) + " vertices of " + std::to_string(vertexSize) + " bytes";
+        vertexCount = 0;
+        body.clear();
+        return false;
+    }
     in.read(reinterpret_cast<char*>(body.data()), static_cast<std::streamsize>(body.size()));
     return true;  // like the reference, a short body is not an error: missing bytes stay zero
 }

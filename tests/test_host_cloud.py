@@ -183,3 +183,17 @@ def test_empty_cloud(splat, oracle, scratch):
     path = _write(scratch / "empty.ply", HEADER_OK.replace(b"vertex 2", b"vertex 0"))
     gc, ok = _import(splat, path)
     assert ok and gc.GetNumGaussians() == 0 and gc.GetTotalSize() == 0
+
+
+@pytest.mark.parametrize("count", ["999999999999", "-5", "18446744073709551615", "4611686018427387904"])
+def test_absurd_vertex_count_is_an_error_not_a_crash(splat, scratch, count):
+    """The reference allocates whatever the header claims (`new uint8_t[size * count]`, ply.cpp:83) and would die on
+    std::bad_alloc; behind a C ABI that must come back as a status code: no exception crosses `extern "C"`."""
+    path = os.path.join(str(scratch), f"absurd_{abs(hash(count)) % 10**6}.ply")
+    header = f"ply\nformat binary_little_endian 1.0\nelement vertex {count}\nproperty float x\nproperty float y\nproperty float z\nend_header\n"
+    with open(path, "wb") as f:
+        f.write(header.encode() + b"\0" * 64)
+    gc = splat.GaussianCloud()
+    assert not gc.ImportPly(path)
+    assert splat.lib().spl_last_error()  # a message, and the process is still alive
+    assert gc.ImportPly(os.path.join(os.path.dirname(__file__), "golden", "reference_test.ply"))  # the object stays usable
