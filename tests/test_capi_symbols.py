@@ -80,3 +80,21 @@ def test_product_never_imports_the_oracle():
                     s = line.strip()
                     if s.startswith(("import ", "from ", "#include")):
                         assert "oracle" not in s, (f, s)
+
+
+def test_header_is_plain_c_and_links(splat, scratch):
+    """include/splat_b200.h compiles as C99 (-pedantic -Werror) and a C program links against the library."""
+    import os
+    import subprocess
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    libdir = os.path.dirname(splat.library_path())
+    exe = os.path.join(str(scratch), "c_abi_consumer")
+    cmd = ["gcc", "-std=c99", "-pedantic", "-Wall", "-Wextra", "-Werror", "-I", os.path.join(root, "include"),
+           os.path.join(root, "tests", "cpp", "c_abi_consumer.c"), "-L", libdir, "-lsplat_b200", f"-Wl,-rpath,{libdir}", "-o", exe]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    out = os.path.join(str(scratch), "pruned.ply")
+    r = subprocess.run([exe, out], capture_output=True, text=True, timeout=60)
+    assert r.returncode == 0, (r.returncode, r.stdout, r.stderr)
+    assert r.stdout.startswith("c abi ok") and os.path.getsize(out) > 0
