@@ -138,8 +138,10 @@ typedef struct spl_stats {
     uint32_t sh_mode;          /* 0 = DC only, 1 = degree 1 (base layout), 3 = degree 3 (FULL_SH) */
     uint32_t sort_mode;        /* SPL_SORT_* the last Sort used */
     uint32_t kernel_launches;  /* kernels launched by the last Sort+Render */
-    float stage_ms[8];         /* profiling on: [0] project [1] LSD: histogram | binned: scan+scatter [2] LSD: scatter passes |
-                                  binned: segment sort [3] LSD: tile ranges [4] composite [7] whole frame */
+    float stage_ms[8];         /* profiling on: [0] project  [1] LSD: depth-digit passes on the gaussians + emission (flat: 0) |
+                                  binned: tile scan + scatter  [2] LSD: tile-digit passes (flat: all passes) | binned:
+                                  segment sort  [3] tile ranges (0 when the last sort pass writes them)  [4] composite
+                                  [7] whole frame */
 } spl_stats;
 SPL_API int spl_renderer_stats(spl_renderer*, spl_stats* out); /* synchronizes the stream */
 SPL_API int spl_renderer_reserve(spl_renderer*, uint64_t instance_capacity);
