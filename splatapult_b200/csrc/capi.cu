@@ -435,10 +435,10 @@ int spl_write_ppm(const char* path, const void* host_fb, int width, int height, 
 {
     return guarded([&]() -> int {
     if (!path || !host_fb || width <= 0 || height <= 0) return set_error(SPL_ERR_ARG, "bad argument");
+    std::vector<unsigned char> row((size_t)width * 3);  // before the file is opened: an allocation failure leaks nothing
     FILE* f = std::fopen(path, "wb");
     if (!f) return set_error(SPL_ERR_IO, std::string("failed to open ") + path);
     std::fprintf(f, "P6\n%d %d\n255\n", width, height);
-    std::vector<unsigned char> row((size_t)width * 3);
     auto to8 = [](float v) { v = v < 0.0f ? 0.0f : (v > 1.0f ? 1.0f : v); return (unsigned char)(v * 255.0f + 0.5f); };
     for (int y = height - 1; y >= 0; y--)  // the framebuffer is bottom-up, images are top-down
     {
