@@ -547,7 +547,8 @@ struct RendererImpl
         out->instance_capacity = capacity;
         out->overflow = c.overflow;
         out->tiles_x = fc.tilesX; out->tiles_y = fc.tilesY; out->tile_size = kTileSize;
-        out->sort_passes = frameSortMode == SPL_SORT_BINNED ? 1 : sortPasses;  // LSD: 4 depth-digit passes + tile-digit passes out->sort_bits = sortBits;
+        out->sort_passes = frameSortMode == SPL_SORT_BINNED ? 1 : sortPasses;  // LSD: 4 depth-digit passes + tile-digit passes
+        out->sort_bits = sortBits;
         out->sort_mode = frameSortMode;
         out->sh_mode = cloud.shMode;
         out->kernel_launches = launches;
