@@ -77,6 +77,17 @@ def main():
         pix_done_entry = np.where((T < args.early_out).any(axis=0), (T < args.early_out).argmax(axis=0) + 1, E)
         ideal_w = pix_done_entry.reshape(4, 4, 2, 8).transpose(0, 2, 1, 3).reshape(8, 32).max(axis=1)
         tile_fin_entry = min(E, (int(first_w.max()) + 1) * 32) if first_w.max() < G else E
+        # finer: entry masks per 4x4 half (or 4x2 quarter) of the warp's block, and the walk skips entries that touch only
+        # halves whose pixels are all finished (liveness refreshed at group boundaries)
+        for name, bh, bw in (("half", 4, 4), ("quarter", 2, 4)):
+            sy, sx = 4 // bh, 8 // bw
+            # [E, warpRow, sy, bh, warpCol, sx, bw]
+            hs = (wgt > 0).reshape(E, 4, sy, bh, 2, sx, bw).any(axis=(3, 6)).transpose(0, 1, 3, 2, 4).reshape(E, 8, sy * sx)
+            fs = first.reshape(4, sy, bh, 2, sx, bw).max(axis=(2, 5)).transpose(0, 2, 1, 3).reshape(8, sy * sx)  # finish group per sub-block
+            gidx = np.arange(E) // 32
+            alive = gidx[:, None, None] <= fs[None, :, :]  # sub-block still has a live pixel while group g <= its finish group
+            tot.setdefault("sub_" + name, 0)
+            tot["sub_" + name] += int((hs & alive).any(axis=2).sum())
         for wi in range(8):
             fin_entry = min(E, (int(first_w[wi]) + 1) * 32) if first_w[wi] < G else E  # entries walked with a live pixel (group granularity)
             now_entry = min(E, ((fin_entry + 255) // 256) * 256)  # the chunk that holds the finishing group is walked to its end
@@ -90,7 +101,7 @@ def main():
         tot["staged_all"] += E
     print(f"tiles sampled {len(sample)}  list entries {tot['entries']}  (early-out T < {args.early_out})")
     print(f"entries staged before the tile stops: {tot['staged_now']} of {tot['staged_all']} ({tot['staged_now'] / tot['staged_all'] * 100:.1f} %)")
-    for k in ("full", "now", "group", "ideal"):
+    for k in ("full", "now", "group", "ideal", "sub_half", "sub_quarter"):
         print(f"trips_{k:6s} {tot[k]:10d}  {tot[k] / tot['now']:.3f} x now")
 
 
