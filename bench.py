@@ -300,6 +300,44 @@ def run_ours(args, rank, local_rank, world):
         r.SetOption(api.OPT_PROFILE, 0)
         st = r.GetStats()
 
+        def timed(fn, steps):
+            """device ms per call of fn, L2 flushed before each call (same procedure as the headline loop)"""
+            for _ in range(3):
+                fn()
+            stream.synchronize()
+            evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+            for a_, b_ in evs:
+                flush.zero_()
+                a_.record(stream)
+                fn()
+                b_.record(stream)
+            stream.synchronize()
+            return float(sum(a_.elapsed_time(b_) for a_, b_ in evs)) / steps
+
+        # ---- informational: exact mode -- no transmittance early-out, the reference's full blend chain per pixel
+        r.SetOption(api.OPT_EARLY_OUT_T, 0.0)
+        exact_ms = timed(frame, args.steps)
+        r.SetOption(api.OPT_EARLY_OUT_T, 1e-4)
+
+        # ---- informational: the VR call pattern (src/app.cpp:603-607): Sort for the left eye, Render for both.  Default:
+        # the second Render sorts again (exact order for each eye); SPL_OPT_SHARED_SORT: the reference's behaviour, the
+        # second eye is re-projected in the left eye's order (no depth passes).  6.4 cm apart, parallel axes.
+        eye_l, eye_r = cam.copy(), cam.copy()
+        right_axis = cam.reshape(4, 4)[0, :3]
+        eye_l.reshape(4, 4)[3, :3] -= 0.032 * right_axis
+        eye_r.reshape(4, 4)[3, :3] += 0.032 * right_axis
+
+        def stereo_pair():
+            r.Sort(eye_l, proj, vp, nf)
+            r.Render(eye_l, proj, vp, nf)
+            r.Render(eye_r, proj, vp, nf)
+
+        stereo_ms = {}
+        for name, opt in (("resort", 0), ("shared_sort", 1)):
+            r.SetOption(api.OPT_SHARED_SORT, opt)
+            stereo_ms[name] = timed(stereo_pair, args.steps)
+        r.SetOption(api.OPT_SHARED_SORT, 0)
+
     if world > 1:
         t = torch.tensor([total_ms, e2e_ms, e2e8_ms], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -377,6 +415,10 @@ def run_ours(args, rank, local_rank, world):
         "clocks": clocks.summary(),
         "e2e": {"value": n * args.steps * world / (e2e_ms * 1e-3) / 1e6, "unit": "Msplats/s", "h2d_bytes_per_step": 38 * 4,
                 "d2h_bytes_per_step": fb_bytes, "ms_per_step": e2e_ms / args.steps, "framebuffer_mean": checksum},
+        "exact_mode": {"ms_per_step": exact_ms, "value": n * world / (exact_ms * 1e-3) / 1e6, "unit": "Msplats/s",
+                       "note": "early_out_T = 0: every list entry of every pixel is blended, as the reference does (rank 0's view)"},
+        "stereo_pair": {"ms_resort": stereo_ms["resort"], "ms_shared_sort": stereo_ms["shared_sort"],
+                        "note": "Sort(left) + Render(left) + Render(right), device time per pair (rank 0's view); shared_sort = the reference's VR behaviour"},
         "e2e_presented_rgba8": {"value": n * args.steps * world / (e2e8_ms * 1e-3) / 1e6, "unit": "Msplats/s", "d2h_bytes_per_step": WIDTH * HEIGHT * 4,
                                 "ms_per_step": e2e8_ms / args.steps,
                                 "note": "informational: same loop, reading the 8-bit presented frame (RenderDesktop blit) instead of the float target"},

@@ -152,8 +152,13 @@ enum {
     SPL_OPT_INSTANCES_PER_GAUSSIAN = 2, /* initial capacity factor, before init (default 16) */
     SPL_OPT_SORT_TILE = 4,    /* keys per onesweep tile: 4096 (default) or 2048 */
     SPL_OPT_SORT_MODE = 3,    /* SPL_SORT_LSD (default), SPL_SORT_LSD_FLAT or SPL_SORT_BINNED; all give bit-identical tile lists */
-    SPL_OPT_SUBBLOCK_CULL = 5 /* compositor's per-entry 8x4 sub-block mask: 0 none, 1 footprint box, 2 exact ellipse (default);
+    SPL_OPT_SUBBLOCK_CULL = 5, /* compositor's per-entry 8x4 sub-block mask: 0 none, 1 footprint box, 2 exact ellipse (default);
                                  culling only skips lanes whose weight is discarded anyway: images are bit-identical */
+    SPL_OPT_SHARED_SORT = 6   /* what a Render does whose arguments differ from the last Sort's (the VR pattern: Sort for
+                                 eye 0, Render for both eyes, src/app.cpp:603-607).  0 (default): sort again for the new
+                                 view -- every image is exactly ordered.  1: the reference's behaviour -- keep the list and
+                                 the depth order of the last Sort and only re-project (default sort path, same viewport);
+                                 the four depth passes of the second eye are saved */
 };
 enum {
     SPL_SORT_BINNED = 0, /* MSD: counting sort on the tile id, then per-tile shared-memory sort of (depthKey, id) */

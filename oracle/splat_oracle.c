@@ -503,22 +503,24 @@ static void radiance_from_sh(const float* g, int full, float vx, float vy, float
 }
 
 /* K1 + K5 + K6 for one gaussian */
-static void project_one(const float* g, int full, int srgb, const orc_frame* fr, orc_record* o)
+/* fs: the frame of the last Sort (pre-sort cull + depth key, K1); fr: the frame of the draw (K5/K6).  The desktop path
+ * passes the same matrices to both (app.cpp:1067-1068); the VR path sorts for eye 0 and draws both eyes (app.cpp:603-607). */
+static void project_one(const float* g, int full, int srgb, const orc_frame* fs, const orc_frame* fr, orc_record* o)
 {
     memset(o, 0, sizeof *o);
     float x = g[OFF_POS], y = g[OFF_POS + 1], z = g[OFF_POS + 2];
     o->alpha = g[OFF_POS + 3];
     /* ---- K1: presort_compute.glsl:42-56 */
     float p[4];
-    mat4_xform_point(fr->mvp, x, y, z, p);
+    mat4_xform_point(fs->mvp, x, y, z, p);
     float depth = p[3];
     float xx = p[0] / depth, yy = p[1] / depth;
     const float CLIP = 1.5f;
     int keep = (depth > 0.0f && xx < CLIP && xx > -CLIP && yy < CLIP && yy > -CLIP);
     /* uint() of a value >= 2^32 is undefined in GLSL and the quad is far-clipped anyway: treat as culled */
-    keep = keep && (depth < fr->zf);
+    keep = keep && (depth < fs->zf);
     if (keep) {
-        float q = (depth / fr->zf) * 4294967296.0f; /* float(keyMax) rounds to 2^32 */
+        float q = (depth / fs->zf) * 4294967296.0f; /* float(keyMax) rounds to 2^32 */
         o->key = 0xFFFFFFFFu - (uint32_t)q;
     }
     /* ---- K5: splat_vert.glsl:153-222 */
@@ -577,7 +579,18 @@ ORC_API void orc_project(const float* aos, size_t n, size_t stride_bytes, int fu
 {
     size_t sf = stride_bytes / 4;
 #pragma omp parallel for schedule(static)
-    for (long long i = 0; i < (long long)n; i++) project_one(aos + (size_t)i * sf, full_sh, srgb, fr, &out[i]);
+    for (long long i = 0; i < (long long)n; i++) project_one(aos + (size_t)i * sf, full_sh, srgb, fr, fr, &out[i]);
+}
+
+/* the VR draw of the eye that was NOT sorted for (app.cpp:603-607): list membership and key from the Sort's frame,
+ * everything the vertex / geometry stages compute from the draw's frame.  orc_sort() on the result gives the
+ * reference's draw order for that eye (the sorted list of the other one, minus what the geometry stage discards). */
+ORC_API void orc_project_shared(const float* aos, size_t n, size_t stride_bytes, int full_sh, int srgb,
+                                const orc_frame* fr_sort, const orc_frame* fr_draw, orc_record* out)
+{
+    size_t sf = stride_bytes / 4;
+#pragma omp parallel for schedule(static)
+    for (long long i = 0; i < (long long)n; i++) project_one(aos + (size_t)i * sf, full_sh, srgb, fr_sort, fr_draw, &out[i]);
 }
 
 /* ------------------------------------------------------------------------------------------------ */

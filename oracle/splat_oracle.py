@@ -50,6 +50,7 @@ def lib() -> C.CDLL:
         L.orc_debug_cloud.argtypes = [C.c_void_p]
         L.orc_frame_constants.argtypes = [fp, fp, fp, fp, C.c_void_p]
         L.orc_project.argtypes = [C.c_void_p, C.c_size_t, C.c_size_t, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+        L.orc_project_shared.argtypes = [C.c_void_p, C.c_size_t, C.c_size_t, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
         L.orc_sort.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p]
         L.orc_sort.restype = C.c_size_t
         for f in (L.orc_composite, L.orc_composite_bruteforce):
@@ -143,6 +144,16 @@ def project(aos: np.ndarray, full_sh: bool, frame: Frame, srgb: bool = False) ->
     n, nf = aos.shape
     rec = np.zeros(n, RECORD_DTYPE)
     lib().orc_project(aos.ctypes.data, n, nf * 4, int(full_sh), int(srgb), frame.buf.ctypes.data, rec.ctypes.data)
+    return rec
+
+
+def project_shared(aos: np.ndarray, full_sh: bool, sort_frame: Frame, draw_frame: Frame, srgb: bool = False) -> np.ndarray:
+    """records of a draw that reuses another view's Sort (src/app.cpp:603-607): cull + key from sort_frame, the rest from draw_frame."""
+    aos = np.ascontiguousarray(aos, np.float32)
+    n, nf = aos.shape
+    rec = np.zeros(n, RECORD_DTYPE)
+    lib().orc_project_shared(aos.ctypes.data, n, nf * 4, int(full_sh), int(srgb), sort_frame.buf.ctypes.data,
+                             draw_frame.buf.ctypes.data, rec.ctypes.data)
     return rec
 
 

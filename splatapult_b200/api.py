@@ -18,6 +18,7 @@ OPT_INSTANCES_PER_GAUSSIAN = 2
 OPT_SORT_MODE = 3
 OPT_SORT_TILE = 4
 OPT_SUBBLOCK_CULL = 5
+OPT_SHARED_SORT = 6
 SORT_BINNED = 0
 SORT_LSD = 1
 SORT_LSD_FLAT = 2

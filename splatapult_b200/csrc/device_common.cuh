@@ -38,12 +38,17 @@ constexpr int kSegSortLargeCap = 12288;
 struct FrameConstants
 {
     float view[16];
-    float mvp[16];
+    float mvp[16];  // of the last Sort: cull + depth key only (presort_compute.glsl:42-56); the draw uses view and proj
     float proj[16];
     float eye[3];
     float W, H, zNear, zFar;
     int width, height, tilesX, tilesY;
     int srgb;
+    // shared sort (the reference's VR path sorts for eye 0 and draws both eyes in that order, src/app.cpp:603-607):
+    float zFarSort;   // far plane of the Sort call (= zFar unless a Render re-projects for another eye)
+    int stereoPass;   // 0: Sort and Render see the same view.  1: Sort of a shared-sort frame (every gaussian that passes
+                      // the pre-sort cull keeps its depth key, whether or not this eye draws it).  2: Render for
+                      // another eye: view/proj/eye/zNear/zFar are that eye's, mvp/zFarSort still the Sort's; no keys.
 };
 
 // cloud packed at Init into coalescing-friendly planes (DESIGN.md "HBM layout")

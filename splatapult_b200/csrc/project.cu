@@ -139,6 +139,7 @@ struct Projected
     uint32_t w, h;    // rectangle size in tiles
     uint32_t refKey;  // 0xFFFFFFFF - uint(depth/far * 2^32)
     bool visible;
+    bool listed;      // passed the pre-sort cull (K1 and depth < far): a member of the reference's sorted list
 };
 
 template <int SH_MODE>
@@ -146,7 +147,7 @@ __device__ __forceinline__ Projected project_gaussian(const PackedCloud& cloud, 
                                                       bool inRange)
 {
     uint32_t count = 0, rx0 = 0, ry0 = 0, rw = 0, rh = 0, refKey = 0;
-    bool visible = false;
+    bool visible = false, listed = false;
 
     if (inRange)
     {
@@ -183,12 +184,13 @@ __device__ __forceinline__ Projected project_gaussian(const PackedCloud& cloud, 
         const float xx = p[0] / depth, yy = p[1] / depth;
         const float CLIP = 1.5f;
         bool keep = (depth > 0.0f && xx < CLIP && xx > -CLIP && yy < CLIP && yy > -CLIP);
-        keep = keep && (depth < fc.zFar);  // uint() overflow is undefined in GLSL; the quad is far-clipped anyway
+        keep = keep && (depth < fc.zFarSort);  // uint() overflow is undefined in GLSL; the quad is far-clipped anyway
         if (keep)
         {
-            const float q = (depth / fc.zFar) * 4294967296.0f;
+            const float q = (depth / fc.zFarSort) * 4294967296.0f;
             refKey = 0xFFFFFFFFu - __float2uint_rz(q);
         }
+        listed = keep;
         // ---- K5/K6 transforms + guard band (splat_vert.glsl:157,200-201 ; splat_geom.glsl:46-54)
         float t[4], p4[4];
         xform_point(fc.view, x, y, z, t);
@@ -273,6 +275,7 @@ __device__ __forceinline__ Projected project_gaussian(const PackedCloud& cloud, 
 
     Projected out;
     out.count = count; out.x0 = rx0; out.y0 = ry0; out.w = rw; out.h = rh; out.refKey = refKey; out.visible = visible;
+    out.listed = listed;
     return out;
 }
 
@@ -642,15 +645,20 @@ k_project_keys(const PackedCloud cloud, const __grid_constant__ FrameConstants f
         const Projected pg = project_gaussian<SH_MODE>(cloud, fc, rec, i, inRange);
         if (inRange)
         {
-            const uint32_t key = pg.count ? pg.refKey : 0xFFFFFFFFu;
-            keys[i] = key;
-            vals[i] = i;
             side[i] = pg.count ? make_uint2(pg.x0 | (pg.y0 << 16), pg.w | (pg.h << 16)) : make_uint2(0u, 0u);
-            smem_red_add(&sDigit0[key & (kRadixSize - 1)], 1u);
+            if (fc.stereoPass != 2)
+            {
+                // shared sort: the order must hold for an eye that may draw what this one does not
+                const bool sorted = fc.stereoPass == 1 ? pg.listed : pg.count != 0;
+                const uint32_t key = sorted ? pg.refKey : 0xFFFFFFFFu;
+                keys[i] = key;
+                vals[i] = i;
+                smem_red_add(&sDigit0[key & (kRadixSize - 1)], 1u);
+            }
         }
         visibleMine += pg.visible ? 1u : 0u;
     }
-    if (blockIdx.x == 0 && tid == 0) ctr->sortCount = cloud.n;
+    if (fc.stereoPass != 2 && blockIdx.x == 0 && tid == 0) ctr->sortCount = cloud.n;
     // CTA total of the visible counts: warp reduce, then one atomic per warp into shared memory, one global atomic
     __shared__ uint32_t sVisible;
     if (tid == 0) sVisible = 0;
@@ -661,7 +669,7 @@ k_project_keys(const PackedCloud cloud, const __grid_constant__ FrameConstants f
     __syncthreads();
     if (tid == 0 && sVisible) atomicAdd(&ctr->visible, sVisible);
     const uint32_t c = sDigit0[tid];
-    if (c) atomicAdd(digit0Hist + tid, c);
+    if (c) atomicAdd(digit0Hist + tid, c);  // all zero in a render-only pass
 }
 
 // ---------------------------------------------------------------------------------------------------

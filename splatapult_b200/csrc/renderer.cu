@@ -86,7 +86,11 @@ struct RendererImpl
     // last frame
     bool haveSort = false, haveRender = false;
     FrameConstants fc{};
-    float lastArgs[16 + 16 + 4 + 2] = {};
+    float lastArgs[16 + 16 + 4 + 2] = {};   // arguments of the last Sort
+    float drawArgs[16 + 16 + 4 + 2] = {};   // arguments the current tile lists were built for (= lastArgs unless a
+                                            // shared-sort Render re-projected them for another eye)
+    bool sharedSort = false;                // SPL_OPT_SHARED_SORT: Render for other arguments keeps the last Sort's order
+    uint32_t* dOrder = nullptr;             // shared sort: the depth-sorted gaussian ids of the last Sort (n words)
     int sortPasses = 0, sortBits = 0;
     int frameSortMode = SPL_SORT_LSD;  // sort path the last Sort() used
     bool rangesFused = false;          // dRanges holds {~begin, end} written by the last sort pass (kernels.h)
@@ -134,6 +138,8 @@ struct RendererImpl
         cudaFree(dPresent[0]); cudaFree(dPresent[1]);
         dPresent[0] = dPresent[1] = nullptr;
         presentBytes = 0;
+        cudaFree(dOrder);
+        dOrder = nullptr;
         dPlanes = nullptr; dRec = nullptr; dControl = nullptr; dRanges = nullptr; dFb = dFbs[0] = dFbs[1] = nullptr; dTileCtl = nullptr; dSide = nullptr;
         if (evCreated)
             for (auto& e : ev) cudaEventDestroy(e);
@@ -211,7 +217,8 @@ struct RendererImpl
 
         // drop any previous cloud
         CU_TRY(cudaStreamSynchronize(stream));
-        cudaFree(dPlanes); cudaFree(dRec); cudaFree(dControl); cudaFree(dSide);
+        cudaFree(dPlanes); cudaFree(dRec); cudaFree(dControl); cudaFree(dSide); cudaFree(dOrder);
+        dOrder = nullptr;
         dPlanes = nullptr; dRec = nullptr; dControl = nullptr; dRanges = nullptr; dSide = nullptr;
 
         n = (uint32_t)count;
@@ -253,6 +260,31 @@ struct RendererImpl
         return !std::memcmp(a, cam, 64) && !std::memcmp(a + 16, proj, 64) && !std::memcmp(a + 32, vp, 16) && !std::memcmp(a + 36, nf, 8);
     }
 
+    // default path, second half: expand the depth-ordered gaussian ids into (tile id, id) instances and sort them by
+    // tile (stable passes keep the depth order); the last pass writes the tile ranges.  `order` is dValsA right after the
+    // depth passes, or dOrder when a shared-sort Render re-projects for another eye.
+    int expandAndSortTiles(const uint32_t* order, uint32_t numTiles)
+    {
+        const int tileBits = sortBits - kDepthBits, tilePasses = (tileBits + kRadixBits - 1) / kRadixBits;
+        uint32_t* keysA32 = reinterpret_cast<uint32_t*>(dKeysA);
+        uint32_t* keysB32 = reinterpret_cast<uint32_t*>(dKeysB);
+        CU_TRY(launch_emit_sorted(order, reinterpret_cast<const uint2*>(dSide), n, fc, keysB32, dValsB, dCtr, dScan, (uint32_t)capacity,
+                                  dHist + 4 * kRadixSize, stream));
+        launches += n ? 1 : 0;
+        if (profile) CU_TRY(cudaEventRecord(ev[6], stream));
+        dSortedKeys = dKeysB;
+        dSortedVals = dValsB;
+        sortedKeyBytes = 4;
+        if (tilePasses > 0)
+        {
+            SortWorkspace wsTile{dHist, dStatus, dCtr->sortTickets, capacity, sortGeneration, sortKpt, 4, rangesFused ? dRanges : nullptr, numTiles};
+            CU_TRY(launch_sort_passes32(keysB32, dValsB, keysA32, dValsA, &dCtr->usedInstances, capacity, 0, tileBits, wsTile, numSMs, stream));
+            launches += tilePasses;
+            if (tilePasses & 1) { dSortedKeys = dKeysA; dSortedVals = dValsA; }
+        }
+        return 0;
+    }
+
     int sort(const float* cam, const float* proj, const float* vp, const float* nf)
     {
         if (int rc = begin()) return rc;
@@ -274,7 +306,10 @@ struct RendererImpl
         fc.W = vp[2]; fc.H = vp[3]; fc.zNear = nf[0]; fc.zFar = nf[1];
         fc.width = W; fc.height = H; fc.tilesX = tilesX; fc.tilesY = tilesY;
         fc.srgb = srgb ? 1 : 0;
+        fc.zFarSort = nf[1];
+        fc.stereoPass = (sharedSort && sortMode == SPL_SORT_LSD) ? 1 : 0;
         std::memcpy(lastArgs, cam, 64); std::memcpy(lastArgs + 16, proj, 64); std::memcpy(lastArgs + 32, vp, 16); std::memcpy(lastArgs + 36, nf, 8);
+        std::memcpy(drawArgs, lastArgs, sizeof drawArgs);
 
         const uint32_t numTiles = (uint32_t)tilesX * tilesY;
         if (numTiles > rangesTiles)
@@ -351,7 +386,6 @@ struct RendererImpl
                 // the tile digits are sorted on the D instances, which do not carry the depth key (stable passes keep the
                 // depth order).  Same stable LSD sort of the same (tile | depth) order, half the element-passes at 8 instead
                 // of 12 bytes per element.  The u32 arrays live in the u64 key buffers.
-                const int tileBits = sortBits - kDepthBits, tilePasses = (tileBits + kRadixBits - 1) / kRadixBits;
                 uint32_t* keysA32 = reinterpret_cast<uint32_t*>(dKeysA);
                 uint32_t* keysB32 = reinterpret_cast<uint32_t*>(dKeysB);
                 CU_TRY(launch_project_keys(cloud, fc, dRec, keysA32, dValsA, reinterpret_cast<uint2*>(dSide), dCtr, dHist, stream));
@@ -359,21 +393,15 @@ struct RendererImpl
                 if (profile) CU_TRY(cudaEventRecord(ev[1], stream));
                 SortWorkspace wsDepth{dHist, dStatus, dCtr->sortTickets, capacity, sortGeneration, sortKpt, 0};
                 CU_TRY(launch_sort_passes32(keysA32, dValsA, keysB32, dValsB, &dCtr->sortCount, capacity, 0, kDepthBits, wsDepth, numSMs, stream));
+                launches += 4;
                 // 4 passes: the sorted ids are back in dValsA
-                CU_TRY(launch_emit_sorted(dValsA, reinterpret_cast<const uint2*>(dSide), n, fc, keysB32, dValsB, dCtr, dScan, (uint32_t)capacity,
-                                          dHist + 4 * kRadixSize, stream));
-                launches += 4 + (n ? 1 : 0);
-                if (profile) CU_TRY(cudaEventRecord(ev[6], stream));
-                dSortedKeys = dKeysB;
-                dSortedVals = dValsB;
-                sortedKeyBytes = 4;
-                if (tilePasses > 0)
+                if (fc.stereoPass == 1)
                 {
-                    SortWorkspace wsTile{dHist, dStatus, dCtr->sortTickets, capacity, sortGeneration, sortKpt, 4, rangesFused ? dRanges : nullptr, numTiles};
-                    CU_TRY(launch_sort_passes32(keysB32, dValsB, keysA32, dValsA, &dCtr->usedInstances, capacity, 0, tileBits, wsTile, numSMs, stream));
-                    launches += tilePasses;
-                    if (tilePasses & 1) { dSortedKeys = dKeysA; dSortedVals = dValsA; }
+                    // the tile passes reuse dValsA: keep the depth order for the other eye's Render
+                    if (!dOrder) CU_TRY(cudaMalloc(&dOrder, std::max<size_t>(n, 1) * sizeof(uint32_t)));
+                    CU_TRY(cudaMemcpyAsync(dOrder, dValsA, (size_t)n * sizeof(uint32_t), cudaMemcpyDeviceToDevice, stream));
                 }
+                if (int rc = expandAndSortTiles(dValsA, numTiles)) return rc;
             }
             if (profile) CU_TRY(cudaEventRecord(ev[2], stream));
             if (!rangesFused)
@@ -390,15 +418,62 @@ struct RendererImpl
     const unsigned long long* sortedKeys() const { return dSortedKeys; }
     const uint32_t* sortedVals() const { return dSortedVals; }
 
+    // Render for another eye in the order of the last Sort (src/app.cpp:603-607: Sort for eye 0, Render for both).
+    // The reference's draw re-runs its vertex and geometry stages with the new matrices over the list the Sort left;
+    // here: projection again (records + tile rectangles, no keys), then expansion and tile passes over the kept order.
+    int reproject(const float* cam, const float* proj, const float* vp, const float* nf)
+    {
+        const mat4 camera = mat4::from(cam), projM = mat4::from(proj);
+        const mat4 view = inverse(camera);
+        std::memcpy(fc.view, view.m, 64);  // fc.mvp and fc.zFarSort stay the Sort's
+        std::memcpy(fc.proj, projM.m, 64);
+        fc.eye[0] = camera.at(3, 0); fc.eye[1] = camera.at(3, 1); fc.eye[2] = camera.at(3, 2);
+        fc.zNear = nf[0]; fc.zFar = nf[1];
+        fc.stereoPass = 2;
+        std::memcpy(drawArgs, cam, 64); std::memcpy(drawArgs + 16, proj, 64); std::memcpy(drawArgs + 32, vp, 16); std::memcpy(drawArgs + 36, nf, 8);
+
+        const uint32_t numTiles = (uint32_t)fc.tilesX * fc.tilesY;
+        if (((++sortGeneration) & kSortGenerationMask) == 0)
+        {
+            CU_TRY(cudaMemsetAsync(dStatus, 0, sort_status_bytes(capacity, kMaxSortPasses), stream));
+            ++sortGeneration;
+        }
+        launches = 0;
+        if (profile) CU_TRY(cudaEventRecord(ev[0], stream));
+        CU_TRY(cudaMemsetAsync(dControl, 0, controlBytes, stream));  // counters, histograms, scan state, tile ranges
+        CU_TRY(launch_project_keys(cloud, fc, dRec, nullptr, nullptr, reinterpret_cast<uint2*>(dSide), dCtr, dHist, stream));
+        launches += n ? 1 : 0;
+        if (profile) CU_TRY(cudaEventRecord(ev[1], stream));
+        if (int rc = expandAndSortTiles(dOrder, numTiles)) return rc;
+        if (profile) CU_TRY(cudaEventRecord(ev[2], stream));
+        if (!rangesFused)
+        {
+            CU_TRY(launch_tile_ranges(dSortedKeys, sortedKeyBytes, &dCtr->usedInstances, capacity, dRanges, numTiles, numSMs, stream));
+            launches += 1;
+        }
+        if (profile) CU_TRY(cudaEventRecord(ev[3], stream));
+        return 0;
+    }
+
     int render(const float* cam, const float* proj, const float* vp, const float* nf)
     {
         if (int rc = begin()) return rc;
         if (!initialized) return fail(SPL_ERR_ARG, "Render before Init");
         // The reference's Render re-projects with its own arguments in the order of the last Sort (the VR path
-        // sorts for eye 0 only, src/app.cpp:603-607).  Here projection lives in Sort; a Render whose arguments
-        // differ from the last Sort re-runs Sort so the image is always that of the arguments given.
-        if (!haveSort || !sameArgs(lastArgs, cam, proj, vp, nf))
+        // sorts for eye 0 only, src/app.cpp:603-607).  Here projection lives in Sort: by default a Render whose
+        // arguments differ from those the tile lists were built for sorts again (the image is exactly that of the
+        // arguments given); with SPL_OPT_SHARED_SORT it does what the reference does.
+        if (!haveSort)
+        {
             if (int rc = sort(cam, proj, vp, nf)) return rc;
+        }
+        else if (!sameArgs(drawArgs, cam, proj, vp, nf))
+        {
+            // shared sort (the reference's behaviour): keep the last Sort's list and order, re-project for these
+            // arguments.  Needs the default sort path and the Sort's viewport (same tile grid); otherwise re-sort.
+            const bool canShare = sharedSort && fc.stereoPass != 0 && frameSortMode == SPL_SORT_LSD && !std::memcmp(lastArgs + 32, vp, 16);
+            if (int rc = canShare ? reproject(cam, proj, vp, nf) : sort(cam, proj, vp, nf)) return rc;
+        }
         const size_t need = (size_t)fc.width * fc.height * (fbFormat == SPL_FB_FP16 ? 8 : 16);
         if (need > fbBytes)
         {
@@ -497,10 +572,12 @@ struct RendererImpl
             {
                 if (c.totalInstances > kMaxInstances) return fail(SPL_ERR_OVERFLOW, "frame needs more than 2^30 tile instances");
                 if (int rc = reserve(c.totalInstances + c.totalInstances / 4)) return rc;
-                float a[38];
+                float a[38], d[38];
                 std::memcpy(a, lastArgs, sizeof a);
+                std::memcpy(d, drawArgs, sizeof d);
                 haveSort = false;
-                if (int rc = render(a, a + 16, a + 32, a + 36)) return rc;
+                if (int rc = sort(a, a + 16, a + 32, a + 36)) return rc;
+                if (int rc = render(d, d + 16, d + 32, d + 36)) return rc;  // re-projects when the frame was another eye's
             }
         }
         // device -> host on the copy stream, ordered after the composite of this target by an event; the next
@@ -764,6 +841,11 @@ bool SplatRenderer::SetOption(int option, double value)
     case SPL_OPT_SORT_MODE:
         if (value != SPL_SORT_BINNED && value != SPL_SORT_LSD && value != SPL_SORT_LSD_FLAT) { status = SPL_ERR_ARG; error = "unknown sort mode"; return false; }
         impl->sortMode = (int)value;
+        impl->haveSort = false;
+        break;
+    case SPL_OPT_SHARED_SORT:
+        if (value != 0 && value != 1) { status = SPL_ERR_ARG; error = "shared sort must be 0 or 1"; return false; }
+        impl->sharedSort = value != 0;
         impl->haveSort = false;
         break;
     case SPL_OPT_SUBBLOCK_CULL:
