@@ -177,6 +177,22 @@ enum {
 };
 SPL_API int spl_renderer_tap(spl_renderer*, int what, void* host, size_t bytes);
 
+/* ---------------------------------------------------------------- multi-GPU start-up
+ * One renderer per GPU (a process or a thread per GPU); views shard one per GPU; the cloud is replicated ONCE by an
+ * ncclBroadcast over NVLink / NVSwitch -- the multi-GPU form of App::Init's load + SplatRenderer::Init
+ * (src/app.cpp:535-559).  No call on the frame path is collective.  NCCL is loaded at run time (libnccl.so.2). */
+typedef struct spl_comm spl_comm;
+#define SPL_COMM_ID_BYTES 128 /* sizeof(ncclUniqueId) */
+SPL_API int spl_comm_get_unique_id(unsigned char id[SPL_COMM_ID_BYTES]); /* on one rank; ship the bytes to the others */
+SPL_API spl_comm* spl_comm_create(const unsigned char id[SPL_COMM_ID_BYTES], int rank, int nranks, int device); /* collective */
+SPL_API void spl_comm_destroy(spl_comm*);
+SPL_API int spl_comm_nccl_version(void); /* ncclGetVersion() of the loaded copy; 0: NCCL could not be loaded */
+/* collective: every rank calls it, `root` passes its imported cloud, the others NULL.  = spl_renderer_init on every rank
+ * from one host copy of the cloud.  The renderer must have been configured for the communicator's device.
+ * broadcast_ms (optional): device time of the ncclBroadcast of the AoS. */
+SPL_API int spl_renderer_init_broadcast(spl_renderer*, spl_comm*, const spl_cloud* cloud_on_root, int root,
+                                        int is_framebuffer_srgb_enabled, float* broadcast_ms);
+
 /* ---------------------------------------------------------------- CamerasConfig (src/camerasconfig.h:12-32) */
 typedef struct spl_cameras spl_cameras;
 SPL_API spl_cameras* spl_cameras_create(void);
@@ -205,7 +221,14 @@ SPL_API int spl_write_ppm(const char* path, const void* host_fb, int width, int 
 
 /* pinned host memory for the end-to-end path */
 SPL_API void* spl_host_alloc(size_t bytes);
-SPL_API void spl_host_free(void*);
+/* same, with its pages on the NUMA node the GPU `device` hangs off (2-socket hosts: a framebuffer destination on the
+ * other socket makes every D->H copy cross the socket interconnect); plain pinned memory when the node is unknown */
+SPL_API void* spl_host_alloc_near(size_t bytes, int device);
+SPL_API void spl_host_free(void*); /* frees blocks of either allocator */
+SPL_API int spl_device_numa_node(int device); /* NUMA node of the GPU, -1 if the platform reports none */
+/* move the calling thread to the CPUs of the GPU's NUMA node (sched_setaffinity); returns the node, or -1 if nothing
+ * was changed.  Call it first thing in a rank's thread / process, before allocating host buffers. */
+SPL_API int spl_bind_thread_near(int device);
 
 #ifdef __cplusplus
 }

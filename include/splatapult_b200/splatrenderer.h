@@ -14,6 +14,7 @@
 #include "splatmath.h"
 
 struct spl_stats;
+class SplatComm;  // splatcomm.h
 
 namespace splat { struct RendererImpl; }
 
@@ -38,6 +39,13 @@ public:
     // GaussianCloud(opt).ImportPly(file) + Init(cloud, ...) without the host decode: header parsed on the host, the raw
     // PLY body decoded by a CUDA kernel straight into device memory (same records as ImportPly, csrc/plydecode.cu)
     bool InitFromPly(const std::string& plyFilename, bool importFullSH, bool isFramebufferSRGBEnabledIn);
+
+    // multi-GPU start-up (one renderer per GPU, one rank per renderer): EVERY rank of `comm` calls this; the rank `root`
+    // passes the imported cloud, the others nullptr.  The reference-layout AoS travels by ONE ncclBroadcast into device
+    // memory and is packed there (= Init on every rank, with a single host copy of the cloud in the whole job).
+    // broadcastMs (optional): device time of the ncclBroadcast.  The renderer must be Configure()d for comm.Device().
+    bool InitBroadcast(SplatComm& comm, std::shared_ptr<GaussianCloud> cloudOnRoot, int root, bool isFramebufferSRGBEnabledIn,
+                       float* broadcastMs = nullptr);
 
     // reference signatures (src/splatrenderer.h:32-37); viewport = (x, y, width, height)
     void Sort(const splat::mat4& cameraMat, const splat::mat4& projMat, const splat::vec4& viewport, const splat::vec2& nearFar);

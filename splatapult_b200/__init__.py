@@ -10,10 +10,13 @@ from .api import (  # noqa: F401
     FB_FP16,
     FB_FP32,
     GaussianCloud,
+    SplatComm,
     SplatError,
     SplatRenderer,
     Stats,
+    bind_thread_near,
     device_count,
+    device_numa_node,
     host_alloc,
     lib,
     library_path,

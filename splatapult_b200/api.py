@@ -110,8 +110,17 @@ _SIGNATURES = [
     ("spl_sort_pairs_host", C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     ("spl_write_ppm", C.c_int, [C.c_char_p, C.c_void_p, C.c_int, C.c_int, C.c_int]),
     ("spl_host_alloc", C.c_void_p, [C.c_size_t]),
+    ("spl_host_alloc_near", C.c_void_p, [C.c_size_t, C.c_int]),
     ("spl_host_free", None, [C.c_void_p]),
+    ("spl_device_numa_node", C.c_int, [C.c_int]),
+    ("spl_bind_thread_near", C.c_int, [C.c_int]),
+    ("spl_comm_get_unique_id", C.c_int, [C.c_char_p]),
+    ("spl_comm_create", C.c_void_p, [C.c_char_p, C.c_int, C.c_int, C.c_int]),
+    ("spl_comm_destroy", None, [C.c_void_p]),
+    ("spl_comm_nccl_version", C.c_int, []),
+    ("spl_renderer_init_broadcast", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, _FP]),
 ]
+COMM_ID_BYTES = 128
 EXPORTED_SYMBOLS = [s[0] for s in _SIGNATURES]
 
 _lib = None
@@ -266,6 +275,14 @@ class SplatRenderer:
     def InitFromDevice(self, device_ptr: int, num_gaussians: int, stride: int, has_full_sh: bool, srgb: bool = False) -> None:
         _check(lib().spl_renderer_init_device_aos(self._h, C.c_void_p(device_ptr), num_gaussians, stride, int(has_full_sh), int(srgb)))
 
+    def InitBroadcast(self, comm: "SplatComm", cloud_on_root: "GaussianCloud | None", root: int = 0, srgb: bool = False) -> float:
+        """collective: every rank calls it; `root` passes its imported cloud, the others None.  One ncclBroadcast of the
+        AoS inside the library (no torch tensor on the path).  Returns the device time of that broadcast in ms."""
+        ms = C.c_float(0.0)
+        _check(lib().spl_renderer_init_broadcast(self._h, comm._h, cloud_on_root._h if cloud_on_root is not None else None, int(root), int(srgb),
+                                                 C.byref(ms)))
+        return float(ms.value)
+
     def InitFromPly(self, ply_filename: str, import_full_sh: bool = True, srgb: bool = False) -> None:
         """ImportPly + Init without the host decode: the PLY body is decoded on the device and packed there."""
         _check(lib().spl_renderer_init_ply(self._h, os.fsencode(ply_filename), int(import_full_sh), int(srgb)))
@@ -338,6 +355,36 @@ class SplatRenderer:
         return out
 
 
+class SplatComm:
+    """NCCL communicator of the multi-GPU start-up (include/splatapult_b200/splatcomm.h): one rank per GPU."""
+
+    def __init__(self, unique_id: bytes, rank: int, nranks: int, device: int):
+        if len(unique_id) != COMM_ID_BYTES:
+            raise ValueError("unique id must be 128 bytes")
+        self._h = lib().spl_comm_create(unique_id, int(rank), int(nranks), int(device))
+        if not self._h:
+            raise SplatError(-3, (lib().spl_last_error() or b"").decode(errors="replace"))
+        self.rank, self.nranks, self.device = rank, nranks, device
+
+    @staticmethod
+    def GetUniqueId() -> bytes:
+        buf = C.create_string_buffer(COMM_ID_BYTES)
+        _check(lib().spl_comm_get_unique_id(buf))
+        return buf.raw
+
+    @staticmethod
+    def NcclVersion() -> int:
+        return lib().spl_comm_nccl_version()
+
+    def __del__(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h and _lib is not None:
+            _lib.spl_comm_destroy(h)
+
+    def close(self) -> None:
+        self.__del__()
+
+
 class CamerasConfig:
     """Mirror of the reference's CamerasConfig (src/camerasconfig.h:12-32): INRIA cameras.json -> cameraMat list."""
 
@@ -390,8 +437,8 @@ def write_ppm(path: str, fb: np.ndarray) -> None:
 
 
 class _Pinned:
-    def __init__(self, nbytes: int):
-        self.ptr = lib().spl_host_alloc(nbytes)
+    def __init__(self, nbytes: int, near_device: int | None = None):
+        self.ptr = lib().spl_host_alloc(nbytes) if near_device is None else lib().spl_host_alloc_near(nbytes, int(near_device))
         if not self.ptr:
             raise MemoryError("spl_host_alloc failed")
         self.nbytes = nbytes
@@ -406,6 +453,15 @@ class _Pinned:
             _lib.spl_host_free(C.c_void_p(p))
 
 
-def host_alloc(nbytes: int) -> _Pinned:
-    """pinned host memory (cudaHostAlloc) for the end-to-end path."""
-    return _Pinned(nbytes)
+def host_alloc(nbytes: int, near_device: int | None = None) -> _Pinned:
+    """pinned host memory for the end-to-end path; near_device = d puts its pages on GPU d's NUMA node."""
+    return _Pinned(nbytes, near_device)
+
+
+def bind_thread_near(device: int) -> int:
+    """pin the calling thread to the CPUs of GPU `device`'s NUMA node; returns the node or -1 (nothing changed)."""
+    return lib().spl_bind_thread_near(int(device))
+
+
+def device_numa_node(device: int) -> int:
+    return lib().spl_device_numa_node(int(device))

@@ -35,6 +35,7 @@ CU_SOURCES = {
     "binsort.cu": [],
     "composite.cu": [],
     "renderer.cu": [],
+    "multigpu.cu": [],
     "capi.cu": [],
 }
 CPP_SOURCES = ["ply.cpp", "gaussiancloud.cpp", "camerasconfig.cpp"]

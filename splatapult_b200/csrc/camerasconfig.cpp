@@ -60,12 +60,22 @@ public:
 private:
     const std::string& s;
     size_t p = 0;
+    int depth = 0;  // nesting of the value being parsed: bounded, the parser recurses (a cameras.json nests 3 deep)
+    static constexpr int kMaxDepth = 64;
+    struct DepthGuard
+    {
+        int& d;
+        explicit DepthGuard(int& dd) : d(dd) { ++d; }
+        ~DepthGuard() { --d; }
+    };
     [[noreturn]] void fail(const char* m) const { throw std::runtime_error(std::string("json: ") + m + " at offset " + std::to_string(p)); }
     void ws() { while (p < s.size() && (s[p] == ' ' || s[p] == '\n' || s[p] == '\t' || s[p] == '\r')) p++; }
     bool eat(char c) { ws(); if (p < s.size() && s[p] == c) { p++; return true; } return false; }
     void expect(char c) { if (!eat(c)) fail("unexpected character"); }
     Json value()
     {
+        DepthGuard guard(depth);
+        if (depth > kMaxDepth) fail("nesting deeper than 64 levels");
         ws();
         if (p >= s.size()) fail("unexpected end");
         const char c = s[p];

@@ -9,6 +9,7 @@
 #include <vector>
 
 #include "kernels.h"
+#include "multigpu.h"
 #include "splat_b200.h"
 #include "splatapult_b200/gaussiancloud.h"
 #include "splatapult_b200/splatrenderer.h"
@@ -475,9 +476,69 @@ void* spl_host_alloc(size_t bytes)
     }
     return p;
 }
+void* spl_host_alloc_near(size_t bytes, int device)
+{
+    void* p = nullptr;
+    guarded([&]() -> int {
+        p = splat::host_alloc_near(bytes, device, nullptr);
+        return p ? SPL_OK : set_error(SPL_ERR_ALLOC, "pinned host allocation failed");
+    });
+    return p;
+}
 void spl_host_free(void* p)
 {
-    if (p) cudaFreeHost(p);
+    guarded([&]() -> int { splat::host_free_any(p); return SPL_OK; });
+}
+int spl_device_numa_node(int device) { return splat::numa_node_of_device(device); }
+int spl_bind_thread_near(int device)
+{
+    int node = -1, cpus = 0;
+    int rc = -1;
+    guarded([&]() -> int { rc = splat::bind_thread_near(device, &node, &cpus) ? node : -1; return SPL_OK; });
+    return rc;
+}
+
+// ------------------------------------------------------------------ multi-GPU start-up
+}  // extern "C"
+struct spl_comm
+{
+    SplatComm c;
+};
+extern "C" {
+int spl_comm_get_unique_id(unsigned char id[SPL_COMM_ID_BYTES])
+{
+    return guarded([&]() -> int {
+    if (!id) return set_error(SPL_ERR_ARG, "null argument");
+    std::string err;
+    if (!SplatComm::GetUniqueId(id, &err)) return set_error(SPL_ERR_CUDA, err);
+    return SPL_OK;
+    });
+}
+spl_comm* spl_comm_create(const unsigned char id[SPL_COMM_ID_BYTES], int rank, int nranks, int device)
+{
+    spl_comm* out = nullptr;
+    guarded([&]() -> int {
+    if (!id) return set_error(SPL_ERR_ARG, "null argument");
+    spl_comm* h = new spl_comm;
+    if (!h->c.Init(id, rank, nranks, device))
+    {
+        set_error(SPL_ERR_CUDA, h->c.LastError());
+        delete h;
+        return SPL_ERR_CUDA;
+    }
+    out = h;
+    return SPL_OK;
+    });
+    return out;
+}
+void spl_comm_destroy(spl_comm* h) { delete h; }
+int spl_comm_nccl_version(void) { return SplatComm::NcclVersion(); }
+int spl_renderer_init_broadcast(spl_renderer* h, spl_comm* comm, const spl_cloud* cloud_on_root, int root, int srgb, float* broadcast_ms)
+{
+    return guarded([&]() -> int {
+    if (!h || !comm) return set_error(SPL_ERR_ARG, "null argument");
+    return from_renderer(h, h->r.InitBroadcast(comm->c, cloud_on_root ? cloud_on_root->gc : nullptr, root, srgb != 0, broadcast_ms));
+    });
 }
 
 }  // extern "C"

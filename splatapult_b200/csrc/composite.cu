@@ -77,9 +77,18 @@ struct CompSmem
 template <bool HALF>
 __global__ void __launch_bounds__(kCompThreads, 6)
 k_composite(const uint2* __restrict__ ranges, const uint32_t* __restrict__ vals, int idStride, const ProjRecord* __restrict__ rec,
-            void* __restrict__ fb, int width, int height, int tilesX, float earlyOutT, int cullMode, uint32_t beginXor)
+            void* __restrict__ fb, int width, int height, int tilesX, float earlyOutT, int cullMode, uint32_t beginXor, FrameReport report)
 {
     __shared__ CompSmem s;
+
+    // frame report (renderer.cu: pollReport): the instance count this frame needed, tagged with the frame's sequence number,
+    // posted to a word of mapped host memory -- a fire-and-forget PCIe write, so the host learns about a capacity overflow on
+    // the asynchronous paths without a synchronising read-back.  The counters are final: every producer ran before this kernel.
+    if (report.hostWord && blockIdx.x == 0 && threadIdx.x == 0)
+    {
+        const unsigned long long total = report.counters->totalInstances;
+        *reinterpret_cast<volatile unsigned long long*>(report.hostWord) = report.seqTag | (total < kReportCountMask ? total : kReportCountMask);
+    }
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int tile = blockIdx.x;
@@ -313,14 +322,15 @@ cudaError_t launch_present_rgba8(const void* framebuffer, int fbFormat, uint32_t
 }
 
 cudaError_t launch_composite(const uint2* ranges, const uint32_t* sortedVals, int idStrideWords, const ProjRecord* rec, void* framebuffer,
-                             int fbFormat, int width, int height, int tilesX, int tilesY, float earlyOutT, int cullMode, uint32_t rangeBeginXor, cudaStream_t stream)
+                             int fbFormat, int width, int height, int tilesX, int tilesY, float earlyOutT, int cullMode, uint32_t rangeBeginXor,
+                             const FrameReport& report, cudaStream_t stream)
 {
     const int tiles = tilesX * tilesY;
     if (tiles <= 0) return cudaSuccess;
     if (fbFormat == 1)
-        k_composite<true><<<tiles, kCompThreads, 0, stream>>>(ranges, sortedVals, idStrideWords, rec, framebuffer, width, height, tilesX, earlyOutT, cullMode, rangeBeginXor);
+        k_composite<true><<<tiles, kCompThreads, 0, stream>>>(ranges, sortedVals, idStrideWords, rec, framebuffer, width, height, tilesX, earlyOutT, cullMode, rangeBeginXor, report);
     else
-        k_composite<false><<<tiles, kCompThreads, 0, stream>>>(ranges, sortedVals, idStrideWords, rec, framebuffer, width, height, tilesX, earlyOutT, cullMode, rangeBeginXor);
+        k_composite<false><<<tiles, kCompThreads, 0, stream>>>(ranges, sortedVals, idStrideWords, rec, framebuffer, width, height, tilesX, earlyOutT, cullMode, rangeBeginXor, report);
     return cudaGetLastError();
 }
 

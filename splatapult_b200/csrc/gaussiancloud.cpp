@@ -12,6 +12,7 @@
 #include <cmath>
 #include <cstring>
 #include <fstream>
+#include <new>
 #include <numeric>
 #include <vector>
 
@@ -128,6 +129,8 @@ GaussianCloud::GaussianCloud(const Options& options) : numGaussians(0), gaussian
 
 void GaussianCloud::Allocate(size_t count, size_t stride)
 {
+    // checked: a wrapped product would allocate one float and let the decode loop write `count` records past it
+    if (stride && count > static_cast<size_t>(-1) / stride) throw std::bad_alloc();
     numGaussians = count;
     gaussianSize = stride;
     const size_t floats = count * stride / sizeof(float);

@@ -86,8 +86,18 @@ cudaError_t launch_tile_ranges(const void* sortedKeys, int keyBytes, const uint3
                                uint32_t numTiles, int numSMs, cudaStream_t stream);
 // ids: gaussian id of list entry k is ids[k * idStrideWords] (1: u32 payload array of the LSD sort, 2: low word of the
 // binned sort's u64 (depthKey << 32 | id) pairs)
+// report: where the frame's instance count is posted for the host (mapped pinned memory; hostWord null = no report)
+struct FrameReport
+{
+    const FrameCounters* counters = nullptr;
+    unsigned long long* hostWord = nullptr;  // device pointer of a mapped host word
+    unsigned long long seqTag = 0;           // frame sequence number << kReportSeqShift
+};
+constexpr int kReportSeqShift = 40;
+constexpr unsigned long long kReportCountMask = (1ull << kReportSeqShift) - 1;
 cudaError_t launch_composite(const uint2* ranges, const uint32_t* ids, int idStrideWords, const ProjRecord* rec, void* framebuffer, int fbFormat,
-                             int width, int height, int tilesX, int tilesY, float earlyOutT, int cullMode, uint32_t rangeBeginXor, cudaStream_t stream);
+                             int width, int height, int tilesX, int tilesY, float earlyOutT, int cullMode, uint32_t rangeBeginXor,
+                             const FrameReport& report, cudaStream_t stream);
 
 // float target -> packed RGBA8 (R in the low byte), same pixel order as the target
 cudaError_t launch_present_rgba8(const void* framebuffer, int fbFormat, uint32_t* out, size_t pixels, cudaStream_t stream);

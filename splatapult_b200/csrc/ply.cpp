@@ -88,9 +88,11 @@ bool Ply::Parse(std::istream& in)
     if (!ParseHeader(in)) return false;
     // a header may claim any vertex count: the reference's `new uint8_t[size * count]` (ply.cpp:83) would throw out
     // of the application; a library reports it
-    if (vertexSize && vertexCount > static_cast<size_t>(-1) / vertexSize)
+    // (also with vertexSize == 0, i.e. no property lines: GaussianCloud::Allocate multiplies the count by ITS stride)
+    constexpr size_t kMaxVertices = (size_t(1) << 31) - 1;  // the renderer refuses more than 2^31 - 1 gaussians anyway
+    if (vertexCount > kMaxVertices || (vertexSize && vertexCount > static_cast<size_t>(-1) / vertexSize))
     {
-        error = "vertex count overflows the address space";
+        error = "vertex count " + std::to_string(vertexCount) + " is out of range (at most 2^31 - 1 vertices)";
         vertexCount = 0;
         return false;
     }

@@ -155,6 +155,9 @@ bool decode_ply_on_device(const unsigned char* hostBody, size_t numVertices, siz
     if (e != cudaSuccess) return fail(cuda_err("cudaSetDevice", e) + " (GPU PLY decode needs a CUDA device; ImportPly is the host path)");
     cudaStream_t stream = static_cast<cudaStream_t>(cudaStream);
     const int recFloats = fullSH ? 61 : 25;
+    // the renderer takes at most 2^31 - 1 gaussians; beyond that the byte counts below (and the 32-bit grid) would wrap
+    if (numVertices >= (size_t(1) << 31) || (vertexSize && numVertices > static_cast<size_t>(-1) / vertexSize))
+        return fail("vertex count " + std::to_string(numVertices) + " is out of range (at most 2^31 - 1 vertices)");
     const size_t bodyBytes = numVertices * vertexSize, aosBytes = numVertices * (size_t)recFloats * sizeof(float);
     unsigned char* dBody = nullptr;
     float* dAos = nullptr;

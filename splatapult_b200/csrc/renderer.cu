@@ -16,10 +16,13 @@
 #include <fstream>
 #include <vector>
 
+#include <nvtx3/nvToolsExt.h>  // header-only NVTX v3: a no-op unless a profiler injects itself
+
 #include "kernels.h"
 #include "plydecode.h"
 #include "splat_b200.h"
 #include "splatapult_b200/ply.h"
+#include "splatapult_b200/splatcomm.h"
 
 namespace splat
 {
@@ -30,6 +33,15 @@ namespace splat
         cudaError_t e__ = (expr);                                                                    \
         if (e__ != cudaSuccess) return fail(SPL_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e__)); \
     } while (0)
+
+// host-side range, closed on every exit path (the CU_TRY macro returns early)
+struct NvtxScope
+{
+    explicit NvtxScope(const char* name) { nvtxRangePushA(name); }
+    ~NvtxScope() { nvtxRangePop(); }
+    NvtxScope(const NvtxScope&) = delete;
+    NvtxScope& operator=(const NvtxScope&) = delete;
+};
 
 struct RendererImpl
 {
@@ -98,6 +110,17 @@ struct RendererImpl
     cudaEvent_t ev[7] = {};
     bool evCreated = false;
 
+    // frame reports: the compositor posts {frames composited, instances the frame needed} into mapped host memory, so a
+    // capacity overflow on the ASYNCHRONOUS paths (Render + GetFramebuffer, ReadFramebufferAsync) is noticed without a
+    // synchronising read-back: see pollReports()
+    static constexpr int kReportRing = 64;
+    unsigned long long* hReport = nullptr;  // [kReportRing] ring of (seq << kReportSeqShift | instances needed)
+    unsigned long long* dReport = nullptr;  // device address of hReport
+    uint64_t frameSeq = 0;                  // frames composited so far (the newest frame's sequence number)
+    uint64_t checkedSeq = 0;                // newest frame whose report has been looked at
+    uint64_t seqCapacity[kReportRing] = {}; // capacity frame (seq % kReportRing) ran with
+    uint64_t growTo = 0;                    // capacity the next Sort must reserve (an earlier frame overflowed)
+
     int status = 0;
     std::string error;
 
@@ -123,7 +146,7 @@ struct RendererImpl
     }
     void release()
     {
-        if (!initialized && !stream && !dFb) return;
+        if (!initialized && !stream && !dFb && !hReport) return;
         cudaSetDevice(device);
         if (stream) cudaStreamSynchronize(stream);
         if (copyStream)
@@ -148,6 +171,8 @@ struct RendererImpl
         stream = nullptr;
         ownStream = false;
         initialized = false;
+        if (hReport) cudaFreeHost(hReport);
+        hReport = dReport = nullptr;
     }
 
     int begin()
@@ -159,8 +184,51 @@ struct RendererImpl
             CU_TRY(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
             ownStream = true;
         }
+        if (!hReport)
+        {
+            CU_TRY(cudaHostAlloc(reinterpret_cast<void**>(&hReport), kReportRing * sizeof(unsigned long long), cudaHostAllocMapped | cudaHostAllocPortable));
+            std::memset(hReport, 0, kReportRing * sizeof(unsigned long long));
+            CU_TRY(cudaHostGetDevicePointer(reinterpret_cast<void**>(&dReport), hReport, 0));
+        }
         return 0;
     }
+
+    // Look at the frame reports that have landed since the last call.  Returns the number of frames found INCOMPLETE (they
+    // needed more tile instances than the capacity they ran with; the nearest splats are the ones missing) and writes a
+    // message naming them; schedules the capacity growth for the next Sort.  Costs a few host loads, no CUDA call.
+    int pollReports(std::string* msg)
+    {
+        if (!hReport || frameSeq == checkedSeq) return 0;
+        int incomplete = 0;
+        uint64_t need = 0, firstBad = 0, cap = 0;
+        // reports land in frame order; walk from the oldest unchecked frame that can still be in the ring
+        uint64_t s0 = checkedSeq + 1;
+        if (frameSeq - checkedSeq > (uint64_t)kReportRing) s0 = frameSeq - kReportRing + 1;
+        for (uint64_t q = s0; q <= frameSeq; q++)
+        {
+            const unsigned long long v = *reinterpret_cast<volatile unsigned long long*>(hReport + q % kReportRing);
+            if ((v >> kReportSeqShift) != (q & ((1ull << (64 - kReportSeqShift)) - 1))) break;  // not landed yet
+            checkedSeq = q;
+            const uint64_t total = v & kReportCountMask;
+            if (total > seqCapacity[q % kReportRing])
+            {
+                if (!incomplete) { firstBad = q; cap = seqCapacity[q % kReportRing]; }
+                incomplete++;
+                need = std::max<uint64_t>(need, total);
+            }
+        }
+        if (incomplete)
+        {
+            growTo = std::max<uint64_t>(growTo, need + need / 4);
+            if (msg)
+                *msg = std::to_string(incomplete) + " frame(s) (first: frame " + std::to_string(firstBad) + ") needed up to " + std::to_string(need) +
+                       " tile instances but ran with a capacity of " + std::to_string(cap) +
+                       ": those images are incomplete (nearest splats missing); the capacity is raised before the next Sort";
+        }
+        return incomplete;
+    }
+    // a frame the caller is about to replace (blocking read-back re-renders it): its report must not be raised again
+    void forgetReports() { checkedSeq = frameSeq; }
 
     int reserve(uint64_t want)
     {
@@ -255,6 +323,56 @@ struct RendererImpl
         return rc;
     }
 
+    // multi-GPU start-up: metadata and the AoS travel by ncclBroadcast (NVLink 5 / NVSwitch), device memory to device memory
+    int initBroadcast(SplatComm& comm, const GaussianCloud* cloudOnRoot, int root, bool srgbIn, float* broadcastMs)
+    {
+        if (int rc = begin()) return rc;
+        if (!comm.Ok()) return fail(SPL_ERR_ARG, "InitBroadcast: communicator not initialised");
+        if (comm.Device() != device) return fail(SPL_ERR_ARG, "InitBroadcast: the renderer is configured for device " + std::to_string(device) + ", the communicator for " + std::to_string(comm.Device()));
+        const bool isRoot = comm.Rank() == root;
+        if (isRoot && !cloudOnRoot) return fail(SPL_ERR_ARG, "InitBroadcast: the root rank must pass the cloud");
+        unsigned long long meta[4] = {0, 0, 0, 0};
+        if (isRoot)
+        {
+            meta[0] = cloudOnRoot->GetNumGaussians();
+            meta[1] = cloudOnRoot->GetStride();
+            meta[2] = (cloudOnRoot->HasFullSH() && cloudOnRoot->GetStride() == 244) ? 1 : 0;
+            meta[3] = 0x53504c4154ull;  // "SPLAT"
+        }
+        unsigned long long* dMeta = nullptr;
+        CU_TRY(cudaMalloc(&dMeta, sizeof meta));
+        int rc = 0;
+        void* dAos = nullptr;
+        cudaEvent_t e0 = nullptr, e1 = nullptr;
+        auto run = [&]() -> int {
+            CU_TRY(cudaMemcpyAsync(dMeta, meta, sizeof meta, cudaMemcpyHostToDevice, stream));
+            if (!comm.Broadcast(dMeta, sizeof meta, root, stream)) return fail(SPL_ERR_CUDA, comm.LastError());
+            CU_TRY(cudaMemcpyAsync(meta, dMeta, sizeof meta, cudaMemcpyDeviceToHost, stream));
+            CU_TRY(cudaStreamSynchronize(stream));
+            if (meta[3] != 0x53504c4154ull) return fail(SPL_ERR_ARG, "InitBroadcast: the root rank did not provide a cloud");
+            const size_t count = (size_t)meta[0], stride = (size_t)meta[1];
+            if (count >= (1ull << 31) || (stride != 100 && stride != 244)) return fail(SPL_ERR_ARG, "InitBroadcast: bad cloud metadata");
+            const size_t bytes = count * stride;
+            CU_TRY(cudaMalloc(&dAos, std::max<size_t>(bytes, 16)));
+            if (isRoot && bytes) CU_TRY(cudaMemcpyAsync(dAos, cloudOnRoot->GetRawDataPtr(), bytes, cudaMemcpyHostToDevice, stream));
+            CU_TRY(cudaEventCreate(&e0));
+            CU_TRY(cudaEventCreate(&e1));
+            CU_TRY(cudaEventRecord(e0, stream));
+            if (bytes && !comm.Broadcast(dAos, bytes, root, stream)) return fail(SPL_ERR_CUDA, comm.LastError());
+            CU_TRY(cudaEventRecord(e1, stream));
+            CU_TRY(cudaStreamSynchronize(stream));
+            if (broadcastMs) CU_TRY(cudaEventElapsedTime(broadcastMs, e0, e1));
+            return initFromDevice(dAos, count, stride, meta[2] != 0, srgbIn);
+        };
+        rc = run();
+        cudaStreamSynchronize(stream);
+        if (e0) cudaEventDestroy(e0);
+        if (e1) cudaEventDestroy(e1);
+        cudaFree(dAos);
+        cudaFree(dMeta);
+        return rc;
+    }
+
     static bool sameArgs(const float* a, const float* cam, const float* proj, const float* vp, const float* nf)
     {
         return !std::memcmp(a, cam, 64) && !std::memcmp(a + 16, proj, 64) && !std::memcmp(a + 32, vp, 16) && !std::memcmp(a + 36, nf, 8);
@@ -285,10 +403,32 @@ struct RendererImpl
         return 0;
     }
 
+    // Public entry points = poll the frame reports, do the work, and hand back SPL_ERR_OVERFLOW as a NOTIFICATION when an
+    // earlier asynchronous frame turned out to be incomplete (the call itself has been carried out, with the capacity raised).
     int sort(const float* cam, const float* proj, const float* vp, const float* nf)
+    {
+        std::string rep;
+        const int incomplete = pollReports(&rep);
+        if (int rc = sortImpl(cam, proj, vp, nf)) return rc;
+        return incomplete ? fail(SPL_ERR_OVERFLOW, rep) : ok();
+    }
+    int render(const float* cam, const float* proj, const float* vp, const float* nf)
+    {
+        std::string rep;
+        const int incomplete = pollReports(&rep);
+        if (int rc = renderImpl(cam, proj, vp, nf)) return rc;
+        return incomplete ? fail(SPL_ERR_OVERFLOW, rep) : ok();
+    }
+
+    int sortImpl(const float* cam, const float* proj, const float* vp, const float* nf)
     {
         if (int rc = begin()) return rc;
         if (!initialized) return fail(SPL_ERR_ARG, "Sort before Init");
+        if (growTo > capacity)
+        {
+            if (int rc = reserve(growTo)) return rc;  // an earlier frame overflowed (pollReports)
+        }
+        growTo = 0;
         if (vp[0] != 0.0f || vp[1] != 0.0f) return fail(SPL_ERR_ARG, "viewport origin must be (0,0) (the reference assumes it, SURVEY q6)");
         const int W = (int)vp[2], H = (int)vp[3];
         if (W <= 0 || H <= 0 || (float)W != vp[2] || (float)H != vp[3]) return fail(SPL_ERR_ARG, "viewport width/height must be positive integers");
@@ -343,7 +483,11 @@ struct RendererImpl
             uint32_t* tileCursor = dTileCtl + rangesTiles;
             uint32_t* largeList = dTileCtl + 2 * (size_t)rangesTiles;
             CU_TRY(cudaMemsetAsync(tileCount, 0, (size_t)numTiles * sizeof(uint32_t), stream));
-            CU_TRY(launch_project_bin(cloud, fc, dRec, dSide, tileCount, dCtr, stream));
+            nvtxRangePushA("pre-sort");
+            const cudaError_t pe = launch_project_bin(cloud, fc, dRec, dSide, tileCount, dCtr, stream);
+            nvtxRangePop();
+            CU_TRY(pe);
+            NvtxScope sortZone("sort");
             if (profile) CU_TRY(cudaEventRecord(ev[1], stream));
             CU_TRY(launch_tile_scan(tileCount, numTiles, dRanges, tileCursor, largeList, dCtr, (uint32_t)capacity, stream));
             CU_TRY(launch_bin_instances(dSide, n, tilesX, tileCursor, dKeysA, (uint32_t)capacity, stream));
@@ -368,7 +512,11 @@ struct RendererImpl
             {
                 // every digit pass runs on the D tile instances (emitted in gaussian order by the projection kernel,
                 // which also produces the first digit's histogram; pass p produces pass p+1's)
-                CU_TRY(launch_project(cloud, fc, dRec, dKeysA, dValsA, dCtr, dScan, (uint32_t)capacity, dHist, stream));
+                nvtxRangePushA("pre-sort");
+                const cudaError_t pe = launch_project(cloud, fc, dRec, dKeysA, dValsA, dCtr, dScan, (uint32_t)capacity, dHist, stream);
+                nvtxRangePop();
+                CU_TRY(pe);
+                NvtxScope sortZone("sort");
                 launches += n ? 1 : 0;
                 if (profile) CU_TRY(cudaEventRecord(ev[1], stream));
                 if (profile) CU_TRY(cudaEventRecord(ev[6], stream));
@@ -388,9 +536,13 @@ struct RendererImpl
                 // of 12 bytes per element.  The u32 arrays live in the u64 key buffers.
                 uint32_t* keysA32 = reinterpret_cast<uint32_t*>(dKeysA);
                 uint32_t* keysB32 = reinterpret_cast<uint32_t*>(dKeysB);
-                CU_TRY(launch_project_keys(cloud, fc, dRec, keysA32, dValsA, reinterpret_cast<uint2*>(dSide), dCtr, dHist, stream));
+                nvtxRangePushA("pre-sort");  // the reference's zone names (src/splatrenderer.cpp:172,208)
+                const cudaError_t pe = launch_project_keys(cloud, fc, dRec, keysA32, dValsA, reinterpret_cast<uint2*>(dSide), dCtr, dHist, stream);
+                nvtxRangePop();
+                CU_TRY(pe);
                 launches += n ? 1 : 0;
                 if (profile) CU_TRY(cudaEventRecord(ev[1], stream));
+                NvtxScope sortZone("sort");
                 SortWorkspace wsDepth{dHist, dStatus, dCtr->sortTickets, capacity, sortGeneration, sortKpt, 0};
                 CU_TRY(launch_sort_passes32(keysA32, dValsA, keysB32, dValsB, &dCtr->sortCount, capacity, 0, kDepthBits, wsDepth, numSMs, stream));
                 launches += 4;
@@ -455,7 +607,7 @@ struct RendererImpl
         return 0;
     }
 
-    int render(const float* cam, const float* proj, const float* vp, const float* nf)
+    int renderImpl(const float* cam, const float* proj, const float* vp, const float* nf)
     {
         if (int rc = begin()) return rc;
         if (!initialized) return fail(SPL_ERR_ARG, "Render before Init");
@@ -465,14 +617,14 @@ struct RendererImpl
         // arguments given); with SPL_OPT_SHARED_SORT it does what the reference does.
         if (!haveSort)
         {
-            if (int rc = sort(cam, proj, vp, nf)) return rc;
+            if (int rc = sortImpl(cam, proj, vp, nf)) return rc;
         }
         else if (!sameArgs(drawArgs, cam, proj, vp, nf))
         {
             // shared sort (the reference's behaviour): keep the last Sort's list and order, re-project for these
             // arguments.  Needs the default sort path and the Sort's viewport (same tile grid); otherwise re-sort.
             const bool canShare = sharedSort && fc.stereoPass != 0 && frameSortMode == SPL_SORT_LSD && !std::memcmp(lastArgs + 32, vp, 16);
-            if (int rc = canShare ? reproject(cam, proj, vp, nf) : sort(cam, proj, vp, nf)) return rc;
+            if (int rc = canShare ? reproject(cam, proj, vp, nf) : sortImpl(cam, proj, vp, nf)) return rc;
         }
         const size_t need = (size_t)fc.width * fc.height * (fbFormat == SPL_FB_FP16 ? 8 : 16);
         if (need > fbBytes)
@@ -510,8 +662,15 @@ struct RendererImpl
         fbW = fc.width; fbH = fc.height;
         if (profile) CU_TRY(cudaEventRecord(ev[4], stream));
         const bool binned = frameSortMode == SPL_SORT_BINNED;
-        CU_TRY(launch_composite(dRanges, binned ? reinterpret_cast<const uint32_t*>(dKeysA) : sortedVals(), binned ? 2 : 1, dRec, dFb, fbFormat, fc.width, fc.height, fc.tilesX, fc.tilesY, (float)earlyOutT, subblockCull,
-                                rangesFused ? kFusedRangeBeginXor : 0u, stream));
+        const uint64_t seq = frameSeq + 1;
+        const FrameReport report{dCtr, dReport + seq % kReportRing, (seq & ((1ull << (64 - kReportSeqShift)) - 1)) << kReportSeqShift};
+        nvtxRangePushA("draw");  // the reference's zone name (src/splatrenderer.cpp:323)
+        const cudaError_t ce = launch_composite(dRanges, binned ? reinterpret_cast<const uint32_t*>(dKeysA) : sortedVals(), binned ? 2 : 1, dRec, dFb, fbFormat, fc.width,
+                                                fc.height, fc.tilesX, fc.tilesY, (float)earlyOutT, subblockCull, rangesFused ? kFusedRangeBeginXor : 0u, report, stream);
+        nvtxRangePop();
+        CU_TRY(ce);
+        frameSeq = seq;
+        seqCapacity[seq % kReportRing] = capacity;
         launches += 1;
         if (profile) CU_TRY(cudaEventRecord(ev[5], stream));
         CU_TRY(cudaEventRecord(evRendered[target], stream));
@@ -545,6 +704,9 @@ struct RendererImpl
             CU_TRY(cudaEventSynchronize(evCopied[fbCur]));
             copyPending[fbCur] = false;
         }
+        // the frames whose pixels have just landed have also posted their reports
+        std::string rep;
+        if (pollReports(&rep)) return fail(SPL_ERR_OVERFLOW, rep);
         return ok();
     }
 
@@ -576,8 +738,9 @@ struct RendererImpl
                 std::memcpy(a, lastArgs, sizeof a);
                 std::memcpy(d, drawArgs, sizeof d);
                 haveSort = false;
-                if (int rc = sort(a, a + 16, a + 32, a + 36)) return rc;
-                if (int rc = render(d, d + 16, d + 32, d + 36)) return rc;  // re-projects when the frame was another eye's
+                if (int rc = sortImpl(a, a + 16, a + 32, a + 36)) return rc;
+                if (int rc = renderImpl(d, d + 16, d + 32, d + 36)) return rc;  // re-projects when the frame was another eye's
+                forgetReports();  // the incomplete frame has been replaced: nothing to notify
             }
         }
         // device -> host on the copy stream, ordered after the composite of this target by an event; the next
@@ -608,6 +771,8 @@ struct RendererImpl
         CU_TRY(cudaEventRecord(evCopied[fbCur], copyStream));
         copyPending[fbCur] = true;
         if (wait) CU_TRY(cudaStreamSynchronize(copyStream));
+        std::string rep;
+        if (pollReports(&rep)) return fail(SPL_ERR_OVERFLOW, rep);  // notification (the copy has been enqueued / done)
         return ok();
     }
 
@@ -750,6 +915,11 @@ bool SplatRenderer::InitFromDevice(const void* deviceAos, size_t numGaussians, s
     FORWARD(impl->initFromDevice(deviceAos, numGaussians, stride, hasFullSH, isFramebufferSRGBEnabledIn));
 }
 
+bool SplatRenderer::InitBroadcast(SplatComm& comm, std::shared_ptr<GaussianCloud> cloudOnRoot, int root, bool isFramebufferSRGBEnabledIn, float* broadcastMs)
+{
+    FORWARD(impl->initBroadcast(comm, cloudOnRoot.get(), root, isFramebufferSRGBEnabledIn, broadcastMs));
+}
+
 bool SplatRenderer::InitFromPly(const std::string& plyFilename, bool importFullSH, bool isFramebufferSRGBEnabledIn)
 {
     auto failWith = [&](int code, const std::string& msg) { status = code; error = msg; return false; };
@@ -811,6 +981,8 @@ bool SplatRenderer::Synchronize()
     cudaError_t e = cudaStreamSynchronize(impl->stream);
     if (e == cudaSuccess && impl->copyStream) e = cudaStreamSynchronize(impl->copyStream);
     if (e != cudaSuccess) { status = impl->fail(SPL_ERR_CUDA, std::string("cudaStreamSynchronize: ") + cudaGetErrorString(e)); error = impl->error; return false; }
+    std::string rep;
+    if (impl->pollReports(&rep)) { status = impl->fail(SPL_ERR_OVERFLOW, rep); error = impl->error; return false; }  // notification
     status = 0;
     return true;
 }

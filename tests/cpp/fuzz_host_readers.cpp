@@ -66,6 +66,18 @@ int main(int argc, char** argv)
         CamerasConfig cc;
         if (cc.ImportJson(tmpJson)) { okJson++; (void)cc.GetNumCameras(); }
     }
+    // fixed corpus: a header without property lines claiming 2^62 vertices (vertex size 0: the size guard
+    // must still reject it), and a cameras.json nested 200 000 levels deep (the recursive parser must refuse, not overflow)
+    {
+        { std::ofstream f(tmpPly, std::ios::binary); f << "ply\nformat binary_little_endian 1.0\nelement vertex 4611686018427387904\nend_header\n"; }
+        GaussianCloud gc(GaussianCloud::Options{true, true});
+        if (gc.ImportPly(tmpPly)) { std::printf("corpus: huge no-property ply was accepted\n"); return 1; }
+        { std::ofstream f(tmpJson, std::ios::binary); f << std::string(200000, '['); }
+        CamerasConfig cc;
+        if (cc.ImportJson(tmpJson)) { std::printf("corpus: deep json was accepted\n"); return 1; }
+        { std::ofstream f(tmpJson, std::ios::binary); for (int i = 0; i < 100000; i++) f << "{\"a\":"; }
+        if (cc.ImportJson(tmpJson)) { std::printf("corpus: deep json object was accepted\n"); return 1; }
+    }
     std::printf("fuzz done: ply accepted %d, json accepted %d of %d\n", okPly, okJson, iters);
     return 0;
 }

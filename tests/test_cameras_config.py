@@ -84,3 +84,13 @@ def test_empty_array_and_floor_default(splat, scratch):
     n, p = cfg.EstimateFloorPlane()
     np.testing.assert_array_equal(n, [0, 1, 0])
     np.testing.assert_array_equal(p, [0, 0, 0])
+
+
+def test_deeply_nested_json_is_refused_not_a_stack_overflow(splat, scratch):
+    """the parser recurses per nesting level; a file of 200 000 '[' must come back as `false`."""
+    for name, text in (("arrays", "[" * 200_000), ("objects", '{"a":' * 100_000), ("mixed", '[{"a":' * 50_000)):
+        p = scratch / f"deep_{name}.json"
+        p.write_text(text)
+        cfg = splat.CamerasConfig()
+        assert not cfg.ImportJson(str(p))
+        assert "nesting" in cfg.LastError()

@@ -36,11 +36,11 @@ def test_only_the_c_abi_is_exported(splat):
     names = [l.split()[-1] for l in out.splitlines() if " T " in l]
     c_names = [n for n in names if not n.startswith("_Z")]
     assert c_names and all(n.startswith("spl_") for n in c_names), c_names
-    # C++ symbols: exactly the four drop-in classes of include/splatapult_b200/*.h, none of the internals (namespace splat)
+    # C++ symbols: exactly the drop-in classes of include/splatapult_b200/*.h, none of the internals (namespace splat)
     dem = subprocess.run(["nm", "-DC", "--defined-only", splat.library_path()], capture_output=True, text=True).stdout
     cpp = [l.split(" T ", 1)[1] for l in dem.splitlines() if " T " in l and not l.split(" T ", 1)[1].startswith("spl_")]
     classes = {n.split("::")[0] for n in cpp}
-    assert classes == {"GaussianCloud", "SplatRenderer", "CamerasConfig", "Ply"}, classes
+    assert classes == {"GaussianCloud", "SplatRenderer", "CamerasConfig", "Ply", "SplatComm"}, classes
     assert not any(n.startswith("splat::") for n in cpp)
 
 
@@ -98,3 +98,20 @@ def test_header_is_plain_c_and_links(splat, scratch):
     r = subprocess.run([exe, out], capture_output=True, text=True, timeout=60)
     assert r.returncode == 0, (r.returncode, r.stdout, r.stderr)
     assert r.stdout.startswith("c abi ok") and os.path.getsize(out) > 0
+
+
+def test_multigpu_entry_points_without_a_gpu(splat):
+    """NCCL is bound at run time; the NUMA helpers degrade to 'unknown' -- and nothing falls back to a CPU path."""
+    L = splat.lib()
+    v = splat.SplatComm.NcclVersion()
+    assert v == 0 or v >= 21800  # 0: no libnccl.so.2 on this machine; otherwise a real version (2.18+)
+    if splat.device_count() > 0:
+        pytest.skip("a GPU is present")
+    assert splat.device_numa_node(0) == -1
+    assert splat.bind_thread_near(0) == -1
+    assert not L.spl_host_alloc_near(4096, 0)  # pinned memory needs the CUDA driver
+    if v:
+        uid = splat.SplatComm.GetUniqueId()
+        assert len(uid) == 128 and any(uid)
+        with pytest.raises(splat.SplatError):
+            splat.SplatComm(uid, 0, 1, 0)  # ncclCommInitRank needs a device: loud failure

@@ -197,3 +197,17 @@ def test_absurd_vertex_count_is_an_error_not_a_crash(splat, scratch, count):
     assert not gc.ImportPly(path)
     assert splat.lib().spl_last_error()  # a message, and the process is still alive
     assert gc.ImportPly(os.path.join(os.path.dirname(__file__), "golden", "reference_test.ply"))  # the object stays usable
+
+
+@pytest.mark.parametrize("count", ["4611686018427387904", "2147483648", "75489476129874"])
+def test_huge_vertex_count_without_properties(splat, scratch, count):
+    """ADVICE r1: with NO property lines the vertex size is 0, so the size guard in Ply::Parse did not apply and
+    GaussianCloud::Allocate's count * stride wrapped (one float allocated, `count` records written).  Counts beyond what
+    the renderer accepts (2^31 - 1) are rejected in the reader; Allocate's product is checked."""
+    path = os.path.join(str(scratch), f"noprops_{count}.ply")
+    with open(path, "wb") as f:
+        f.write(f"ply\nformat binary_little_endian 1.0\nelement vertex {count}\nend_header\n".encode())
+    gc = splat.GaussianCloud()
+    assert not gc.ImportPly(path)
+    assert b"out of range" in splat.lib().spl_last_error()
+    assert gc.ImportPly(os.path.join(os.path.dirname(__file__), "golden", "reference_test.ply"))
