@@ -355,12 +355,37 @@ class SplatRenderer:
         return out
 
 
+_nccl_preloaded = False
+
+
+def _preload_nccl() -> None:
+    """libsplat_b200.so binds NCCL at run time by SONAME (libnccl.so.2).  A Python process may import torch AFTER that, and
+    torch's libtorch_cuda.so needs the libnccl.so.2 it was built with (the pip package nvidia-nccl, same SONAME as a system
+    copy): if that package exists, load it first, so that one copy serves both.  A C++ host simply gets the system's."""
+    global _nccl_preloaded
+    if _nccl_preloaded:
+        return
+    _nccl_preloaded = True
+    try:
+        import importlib.util
+
+        spec = importlib.util.find_spec("nvidia")
+        for base in (spec.submodule_search_locations if spec else []):
+            cand = os.path.join(base, "nccl", "lib", "libnccl.so.2")
+            if os.path.exists(cand):
+                C.CDLL(cand, mode=C.RTLD_GLOBAL)
+                return
+    except Exception:  # noqa: BLE001 -- best effort: the library's own dlopen still finds a system copy
+        pass
+
+
 class SplatComm:
     """NCCL communicator of the multi-GPU start-up (include/splatapult_b200/splatcomm.h): one rank per GPU."""
 
     def __init__(self, unique_id: bytes, rank: int, nranks: int, device: int):
         if len(unique_id) != COMM_ID_BYTES:
             raise ValueError("unique id must be 128 bytes")
+        _preload_nccl()
         self._h = lib().spl_comm_create(unique_id, int(rank), int(nranks), int(device))
         if not self._h:
             raise SplatError(-3, (lib().spl_last_error() or b"").decode(errors="replace"))
@@ -368,12 +393,14 @@ class SplatComm:
 
     @staticmethod
     def GetUniqueId() -> bytes:
+        _preload_nccl()
         buf = C.create_string_buffer(COMM_ID_BYTES)
         _check(lib().spl_comm_get_unique_id(buf))
         return buf.raw
 
     @staticmethod
     def NcclVersion() -> int:
+        _preload_nccl()
         return lib().spl_comm_nccl_version()
 
     def __del__(self):

@@ -23,6 +23,7 @@
 
 #include <chrono>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <fstream>
 #include <map>
@@ -58,9 +59,13 @@ static NcclApi& nccl()
     static NcclApi api;
     static std::once_flag once;
     std::call_once(once, [] {
+        // a copy the process already carries (PyTorch's, or one the host linked) wins; SPL_NCCL_LIBRARY names another
         const char* names[] = {"libnccl.so.2", "libnccl.so"};
         for (const char* nm : names)
-            if ((api.handle = dlopen(nm, RTLD_NOW | RTLD_GLOBAL))) break;
+            if ((api.handle = dlopen(nm, RTLD_NOW | RTLD_NOLOAD))) break;
+        if (!api.handle && getenv("SPL_NCCL_LIBRARY")) api.handle = dlopen(getenv("SPL_NCCL_LIBRARY"), RTLD_NOW | RTLD_LOCAL);
+        for (const char* nm : names)
+            if (!api.handle) api.handle = dlopen(nm, RTLD_NOW | RTLD_LOCAL);
         if (!api.handle)
         {
             api.error = std::string("libnccl.so.2 could not be loaded: ") + (dlerror() ? dlerror() : "?");

@@ -32,6 +32,8 @@ def test_reference_arm_prints_one_contract_line(monkeypatch, capsys, tmp_path):
     assert d["value"] > 0 and d["e2e"]["value"] == d["value"] and d["e2e"]["h2d_bytes_per_step"] == 0
     cb = d["cpu_baseline"]
     assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and "3000 of 3000" in cb["sample"]
+    assert cb["omp"]["OMP_PROC_BIND"] == "spread" and set(cb["stage_ms"]) == {"project", "sort", "composite"}
+    assert d["config"]["workload"] == bench.workload_string("tiny")
     assert "workload" in d["config"] and "model" not in d["config"]
 
 
@@ -46,14 +48,45 @@ def test_reference_arm_other_ranks_print_nothing(monkeypatch, capsys, tmp_path):
 
 def test_byte_model():
     n, v, d, tiles, px = 1_000_000, 998_167, 4_221_697, 8160, 1920 * 1080
-    ab = bench.algorithmic_bytes(n, v, d, 0, 6, tiles, px, False, False)
+    ab = bench.algorithmic_bytes(n, v, d, 0, 6, tiles, px, False, False, False)
     assert ab["composite"] == 4 * d + 48 * v + 8 * tiles + 16 * px
     assert ab["sort_pass"] == 24 * d and ab["tile_ranges"] == 8 * tiles
     assert ab["frame"] == ab["project"] + ab["sort_histogram"] + 6 * ab["sort_pass"] + ab["tile_ranges"] + ab["composite"]
-    ab3 = bench.algorithmic_bytes(n, v, d, 3, 6, tiles, px, True, False)
+    ab3 = bench.algorithmic_bytes(n, v, d, 3, 6, tiles, px, True, False, False)
     assert ab3["project"] - ab["project"] == (232 - 52) * v and ab["composite"] - ab3["composite"] == 8 * px
-    binned = bench.algorithmic_bytes(n, v, d, 0, 0, tiles, px, False, True)
+    binned = bench.algorithmic_bytes(n, v, d, 0, 0, tiles, px, False, True, False)
     assert set(binned) == {"project", "bin_scatter", "segment_sort", "composite", "frame"}
+    # default path: depth digits sorted on the N gaussians (8-byte pairs), tile digits on the D instances (8-byte instances)
+    sp = bench.algorithmic_bytes(n, v, d, 0, 6, tiles, px, False, False, True)
+    assert sp["sort_pass"] == 16 * d and sp["depth_sort_emit"] == 4 * 16 * n + 12 * n + 8 * d
+    assert sp["frame"] == sp["project"] + sp["depth_sort_emit"] + 2 * sp["sort_pass"] + sp["tile_ranges"] + sp["composite"]
+
+
+def test_both_arms_name_the_workload_identically():
+    """the driver compares config.workload of the two arms byte for byte (same_config was false)"""
+    import inspect
+
+    src = inspect.getsource(bench)
+    assert src.count('"workload": workload_string(') == 2
+    s = bench.workload_string("1m_deg3")
+    assert "configs[2]" in s and "SH degree 3" in s and "1920x1080" in s and "fp32" in s
+
+
+def test_headline_is_the_full_sh_config():
+    assert bench.HEADLINE == "1m_deg3" and bench.WORKLOADS[bench.HEADLINE]["deg"] == 3
+
+
+def test_kernel_sources_sha_guards_traffic_json():
+    """profiles/traffic.json is keyed by a hash of the kernel sources: a capture of other sources must not be reported"""
+    import os
+
+    sha = bench.kernel_sources_sha()
+    assert len(sha) == 16
+    path = os.path.join(bench.ROOT, "profiles", "traffic.json")
+    prof = json.load(open(path))
+    assert "captures" in prof
+    for name, cap in prof["captures"].items():
+        assert name in bench.WORKLOADS and "kernel_sources_sha" in cap and "dram_bytes_per_launch" in cap
 
 
 def test_cameras_per_rank():

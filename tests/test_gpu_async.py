@@ -126,3 +126,59 @@ def test_presented_rgba8_is_the_desktop_blit(splat, golden_dir, fb_format):
         np.testing.assert_array_equal(pinned[k].array(np.uint8, (180, 320, 4)), wants[k])
     with pytest.raises(api.SplatError):
         r.ReadPresented8Async(pinned[0].ptr, 16)
+
+
+def test_overflow_on_the_async_path_is_reported_and_repaired(splat, oracle, scratch):
+    """with D > capacity the entries that do not fit are the NEAREST splats, and on the asynchronous
+    paths (Render + GetFramebuffer, ReadFramebufferAsync) nothing used to say so.  Now the compositor posts the frame's
+    instance count into mapped host memory; the next host-side wait / Sort raises SPL_ERR_OVERFLOW as a notification,
+    the capacity is grown before the next Sort, and the frames after that are complete."""
+    a = scenes.synthetic_cloud_arrays(3000, 0, seed=5, half_extent=1.0)
+    a["log_scale"] += 2.0
+    path = scenes.write_ply_from_arrays(str(scratch / "async_overflow.ply"), a)
+    gc = splat.GaussianCloud()
+    assert gc.ImportPly(path)
+    r = splat.SplatRenderer()
+    r.SetOption(api.OPT_INSTANCES_PER_GAUSSIAN, 1.0)
+    assert r.Init(gc, False, False)
+    w, h = 640, 480
+    cam, proj = scenes.translate(0, 0, 4), scenes.perspective(scenes.FOVY, w / h)
+    vp, nf = [0, 0, w, h], [scenes.Z_NEAR, scenes.Z_FAR]
+    pin = [splat.host_alloc(w * h * 16), splat.host_alloc(w * h * 16)]
+    r.Sort(cam, proj, vp, nf)
+    r.Render(cam, proj, vp, nf)
+    r.ReadFramebufferAsync(pin[0].ptr, w * h * 16)
+    with pytest.raises(splat.SplatError) as e:
+        r.WaitCopies(0)  # the pixels have landed -- and so has the report that they are incomplete
+    assert e.value.code == -4 and "incomplete" in str(e.value)
+    cap0 = r.GetStats().instance_capacity
+    # the next frame runs with the raised capacity; no further notification
+    r.Sort(cam, proj, vp, nf)
+    r.Render(cam, proj, vp, nf)
+    r.ReadFramebufferAsync(pin[1].ptr, w * h * 16)
+    r.WaitCopies(0)
+    st = r.GetStats()
+    assert not st.overflow and st.instance_capacity > cap0 and st.instance_capacity >= st.num_instances
+    aos, full = oracle.import_ply(path, True)
+    want = oracle.render(aos, full, cam, proj, vp, nf)
+    got = pin[1].array(np.float32, (h, w, 4))
+    d = np.abs(got[..., :3] - want[..., :3])
+    assert d.max() <= 5e-3 and d.mean() <= 1e-4
+    bad = pin[0].array(np.float32, (h, w, 4))
+    assert np.abs(bad[..., :3] - want[..., :3]).max() > 5e-3  # the reported frame really was incomplete
+    # a Sort right after an unreported overflow carries the notification too (Render + GetFramebuffer users)
+    r2 = splat.SplatRenderer()
+    r2.SetOption(api.OPT_INSTANCES_PER_GAUSSIAN, 1.0)
+    assert r2.Init(gc, False, False)
+    r2.Sort(cam, proj, vp, nf)
+    r2.Render(cam, proj, vp, nf)
+    r2.Framebuffer()
+    import time
+
+    time.sleep(0.2)  # the frame finishes on its own; nobody synchronises
+    with pytest.raises(splat.SplatError) as e2:
+        r2.Sort(cam, proj, vp, nf)
+    assert e2.value.code == -4
+    r2.Render(cam, proj, vp, nf)  # that Sort WAS carried out, with the capacity raised
+    fb = r2.ReadFramebuffer()
+    assert np.abs(fb[..., :3] - want[..., :3]).max() <= 5e-3
