@@ -28,3 +28,8 @@ except Exception as e:
 PY
 timeout 300 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_reference.json 2> gpurun_out/bench_reference.err
 echo "reference arm: exit $?"; cut -c1-600 gpurun_out/bench_reference.json
+# sanitizers on test-size frames: logs are copied to profiles/r2_sanitizer_*.txt
+for tool in memcheck racecheck synccheck; do
+  timeout 420 compute-sanitizer --tool $tool --print-limit 20 python benchmarks/sanitize_frame.py > gpurun_out/sanitizer_$tool.txt 2>&1
+  echo "sanitizer $tool: exit $?"; tail -4 gpurun_out/sanitizer_$tool.txt
+done

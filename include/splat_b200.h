@@ -133,7 +133,7 @@ typedef struct spl_stats {
     uint64_t num_instances;    /* D: (gaussian,tile) keys emitted this frame */
     uint64_t instance_capacity;
     uint32_t overflow;         /* 1 if D exceeded capacity (frame incomplete; call spl_renderer_reserve) */
-    uint32_t tiles_x, tiles_y, tile_size;
+    uint32_t tiles_x, tiles_y, tile_w, tile_h; /* composite tile grid; a tile is tile_w x tile_h pixels (32 x 16) */
     uint32_t sort_passes, sort_bits;
     uint32_t sh_mode;          /* 0 = DC only, 1 = degree 1 (base layout), 3 = degree 3 (FULL_SH) */
     uint32_t sort_mode;        /* SPL_SORT_* the last Sort used */

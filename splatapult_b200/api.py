@@ -46,7 +46,7 @@ class Stats(C.Structure):
     _fields_ = [
         ("num_gaussians", C.c_uint64), ("num_visible", C.c_uint64), ("num_instances", C.c_uint64),
         ("instance_capacity", C.c_uint64), ("overflow", C.c_uint32),
-        ("tiles_x", C.c_uint32), ("tiles_y", C.c_uint32), ("tile_size", C.c_uint32),
+        ("tiles_x", C.c_uint32), ("tiles_y", C.c_uint32), ("tile_w", C.c_uint32), ("tile_h", C.c_uint32),
         ("sort_passes", C.c_uint32), ("sort_bits", C.c_uint32), ("sh_mode", C.c_uint32), ("sort_mode", C.c_uint32),
         ("kernel_launches", C.c_uint32), ("stage_ms", C.c_float * 8),
     ]

@@ -5,9 +5,9 @@
 // discard iff w <= 1/256, premultiplied output) -> ROP blend GL_ONE, GL_ONE_MINUS_SRC_ALPHA over a target
 // cleared to (0,0,0,1) (K8, src/app.cpp:144-164), strictly back to front.
 //
-// One CTA owns one 16x16-pixel tile (8 warps, each an 8x4 pixel block, one pixel per thread) and walks the
-// tile's sorted list.  The list is stored back-to-front (ascending reference key); the CTA walks it from its
-// END, i.e. front to back, accumulating
+// One CTA owns one 32x16-pixel tile: 8 warps, each an 8x8 pixel block, TWO pixels per thread (lane l: column l & 7, rows
+// l >> 3 and (l >> 3) + 4 of the block).  It walks the tile's sorted list.  The list is stored back-to-front (ascending
+// reference key); the CTA walks it from its END, i.e. front to back, accumulating
 //     C += T * w * rgb ;  T *= (1 - w)
 // which is the closed form of the reference's "over" chain up to float reassociation, and
 // lets a pixel stop once its transmittance T can no longer change the result by more than earlyOutT
@@ -16,10 +16,15 @@
 // The kernel is instruction-issue bound (ncu: profiles/), not HBM bound, so the design minimises issued
 // instructions per (splat, pixel):
 //   * entries are staged 256 at a time into shared memory as the coefficients of log2(weight) in the pixel's offset
-//     from the tile centre (5 FFMA + EX2 per pixel); the gather of the next chunk's records is issued before the
-//     current chunk is evaluated (software pipeline, one barrier per chunk);
-//   * while staging, each entry gets an 8-bit mask of the 8x4 sub-blocks its discard ellipse reaches (exact); a warp
-//     ballots the masks of 32 entries at a time and evaluates only its hits -- warp-uniform, no divergence.
+//     (u, v) from the tile centre; the gather of the next chunk's records is issued before the current chunk is
+//     evaluated (software pipeline, one barrier per chunk);
+//   * while staging, each entry gets an 8-bit mask of the 8x8 blocks its discard ellipse reaches (exact); a warp
+//     ballots the masks of 32 entries at a time and evaluates only its hits -- warp-uniform, no divergence;
+//   * the two pixels of a thread are evaluated with Blackwell's packed FP32 pipe (fma.rn.f32x2 -> SASS FFMA2, whose
+//     operands may each be a scalar broadcast): log2 w = c0 + u (c1 + hA u + hB v) + v (c2 + hC v) is 5 FFMA2 for both
+//     pixels (they share u), the weight and the three colour accumulators 1 FMUL2 + 3 FFMA2 + 1 FADD2 -- a 24-instruction
+//     hit body per 64 pixels where one pixel per thread took 21 per 32; the walk (FLO, BMSK, LOP3, LEA, 3 LDS, BRA) is
+//     paid once per pair.  8x8 blocks are hit by 0.61x as many (entry, block) pairs as 8x4 ones (benchmarks/hit_model.py).
 // Pixel centres are at (x+0.5, y+0.5), row 0 is the bottom row (GL window coordinates).
 #include <cuda_fp16.h>
 
@@ -29,11 +34,43 @@
 namespace splat
 {
 
-constexpr int kCompThreads = kTileSize * kTileSize;  // 256: one thread per pixel
+constexpr int kCompThreads = 256;                    // 8 warps; two pixels per thread
 constexpr int kCompChunk = kCompThreads;             // list entries staged per round (one per thread)
-constexpr int kSubW = 8, kSubH = 4;                  // a warp's pixel block
-constexpr int kSubCols = kTileSize / kSubW;          // 2
-constexpr int kSubRows = kTileSize / kSubH;          // 4
+constexpr int kSubW = 8, kSubH = 8;                  // a warp's pixel block
+constexpr int kSubCols = kTileW / kSubW;             // 4
+constexpr int kSubRows = kTileH / kSubH;             // 2
+static_assert(kSubCols * kSubRows * 32 == kCompThreads, "one warp per 8x8 block");
+static_assert(kSubCols * kSubRows <= 8, "the sub-block mask has 8 bits");
+
+// ---- packed FP32 pairs (Blackwell: one FFMA2 / FMUL2 / FADD2 does two independent fp32 operations; every operand may be a
+// scalar broadcast in the SASS encoding, which the compiler uses when both halves of a pair are the same register)
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pack2(float lo, float hi)
+{
+    f32x2 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ f32x2 bcast2(float s) { return pack2(s, s); }
+__device__ __forceinline__ void unpack2(f32x2 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c)
+{
+    f32x2 d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b)
+{
+    f32x2 d;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ f32x2 sub2(f32x2 a, f32x2 b)
+{
+    f32x2 d;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
 
 // ---------------------------------------------------------------------------------------------------
 // tile ranges: [begin, end) of each tile's run in the sorted key array
@@ -71,7 +108,8 @@ struct CompSmem
     float4 a[2][kCompChunk];    // c0, c1, c2, hA   with  log2 w = c0 + c1 u + c2 v + hA u^2 + hB uv + hC v^2  (stage())
     float4 b[2][kCompChunk];    // hB, hC, r, g
     float4 c[2][kCompChunk];    // b, -, -, -       (same index stride as a/b: one address computation per entry)
-    uint32_t mask[2][kCompChunk];  // bit (row*2+col) set: the splat's ellipse reaches that 8x4 sub-block
+    uint32_t hits[2][kCompChunk / 32][8];  // per group of 32 entries and per warp: the entries whose ellipse reaches that warp's
+                                           // 8x8 block (bit k = entry slot k of the group)
 };
 
 template <bool HALF>
@@ -81,7 +119,7 @@ k_composite(const uint2* __restrict__ ranges, const uint32_t* __restrict__ vals,
 {
     __shared__ CompSmem s;
 
-    // frame report (renderer.cu: pollReport): the instance count this frame needed, tagged with the frame's sequence number,
+    // frame report (renderer.cu: pollReports): the instance count this frame needed, tagged with the frame's sequence number,
     // posted to a word of mapped host memory -- a fire-and-forget PCIe write, so the host learns about a capacity overflow on
     // the asynchronous paths without a synchronising read-back.  The counters are final: every producer ran before this kernel.
     if (report.hostWord && blockIdx.x == 0 && threadIdx.x == 0)
@@ -94,19 +132,26 @@ k_composite(const uint2* __restrict__ ranges, const uint32_t* __restrict__ vals,
     const int tile = blockIdx.x;
     const int tileX = tile % tilesX, tileY = tile / tilesX;
     const int subCol = warp % kSubCols, subRow = warp / kSubCols;
-    const int x = tileX * kTileSize + subCol * kSubW + (lane & (kSubW - 1));
-    const int y = tileY * kTileSize + subRow * kSubH + (lane / kSubW);
-    const bool inside = x < width && y < height;
-    const float tileX0 = (float)(tileX * kTileSize), tileY0 = (float)(tileY * kTileSize);
-    const float tileCx = tileX0 + 0.5f * kTileSize, tileCy = tileY0 + 0.5f * kTileSize;
-    // gl_FragCoord.xy = (x + 0.5, y + 0.5), kept relative to the tile centre
-    const float pu = ((float)x + 0.5f) - tileCx, pv = ((float)y + 0.5f) - tileCy;
-    const float puu = pu * pu, puv = pu * pv, pvv = pv * pv;
+    // this thread's two pixels: same column, rows 4 apart inside the warp's 8x8 block
+    const int x = tileX * kTileW + subCol * kSubW + (lane & (kSubW - 1));
+    const int y0 = tileY * kTileH + subRow * kSubH + (lane / kSubW), y1 = y0 + kSubH / 2;
+    const bool inside0 = x < width && y0 < height, inside1 = x < width && y1 < height;
+    const float tileX0 = (float)(tileX * kTileW), tileY0 = (float)(tileY * kTileH);
+    const float tileCx = tileX0 + 0.5f * kTileW, tileCy = tileY0 + 0.5f * kTileH;
+    // gl_FragCoord.xy = (x + 0.5, y + 0.5), kept relative to the tile centre (|u| <= 15.5, |v| <= 7.5: exact in float)
+    const float pu = ((float)x + 0.5f) - tileCx;
+    const f32x2 pv = pack2(((float)y0 + 0.5f) - tileCy, ((float)y1 + 0.5f) - tileCy);
 
     uint2 range = ranges[tile];
     range.x ^= beginXor;  // ranges written by the last sort pass store ~begin (kernels.h: SortWorkspace::tileRanges)
     // T == 0 marks a finished pixel: every later contribution is multiplied by it
-    float T = inside ? 1.0f : 0.0f, cr = 0.0f, cg = 0.0f, cb = 0.0f;
+    f32x2 T = pack2(inside0 ? 1.0f : 0.0f, inside1 ? 1.0f : 0.0f);
+    f32x2 cr = pack2(0.0f, 0.0f), cg = cr, cb = cr;
+    auto live = [&]() {
+        float t0, t1;
+        unpack2(T, t0, t1);
+        return t0 != 0.0f || t1 != 0.0f;
+    };
 
     // software pipeline: the records of chunk k+1 are in flight while chunk k is evaluated
     float4 q0, q1, q2;
@@ -127,15 +172,13 @@ k_composite(const uint2* __restrict__ ranges, const uint32_t* __restrict__ vals,
         // a warp evaluates its hits highest ballot bit first (FLO, no bit reversal): each group of 32 entries is
         // stored in reverse lane order, so the highest bit is the nearest entry
         const int sidx = tid ^ 31;
-        if (!have)
+        uint32_t m = 0u;  // sub-block mask of this thread's entry: bit (row * kSubCols + col) = the warp that owns the block
+        if (have)
         {
-            s.mask[buf][sidx] = 0u;
-            return;
-        }
         // log2 w as a polynomial in the pixel's offset (u, v) from the TILE centre: with d0 = tile centre - splat centre,
         //   log2 w = hA (dx0+u)^2 + hB (dx0+u)(dy0+v) + hC (dy0+v)^2 + L = c0 + c1 u + c2 v + hA u^2 + hB uv + hC v^2
-        // every lane keeps u, v, u^2, uv, v^2 (|u|,|v| <= 7.5, exact in float), so an entry costs 5 FFMA instead of
-        // 2 FADD + 2 FMUL + 3 FFMA; the rounding error is that of the direct form (same term magnitudes).
+        // evaluated per pixel pair as c0 + u (c1 + hA u + hB v) + v (c2 + hC v): 5 FFMA2; the rounding error is that of the
+        // direct form (same term magnitudes).
         const float kLog2e = 1.4426950408889634f;
         const float h = -0.5f * kLog2e;
         const float hA = h * q0.z, hB = h * (q0.w + q1.x), hC = h * q1.y;
@@ -146,7 +189,7 @@ k_composite(const uint2* __restrict__ ranges, const uint32_t* __restrict__ vals,
         s.a[buf][sidx] = make_float4(c0, c1, c2, hA);
         s.b[buf][sidx] = make_float4(hB, hC, q1.z, q1.w);
         s.c[buf][sidx] = make_float4(q2.x, 0.0f, 0.0f, 0.0f);
-        // Sub-block mask: which 8x4 pixel blocks can hold a pixel with alpha exp(-Q/2) > 1/256, i.e. a pixel centre
+        // Sub-block mask: which 8x8 pixel blocks can hold a pixel with alpha exp(-Q/2) > 1/256, i.e. a pixel centre
         // inside the ellipse Q(d) = A dx^2 + 2B dx dy + C dy^2 < r2, r2 = 2 ln(256 alpha) (inflated so rounding in
         // the evaluation below cannot put a contributing pixel outside).  A culled lane would have been discarded
         // anyway (tw = 0 leaves the accumulators bit-unchanged): the image does not depend on the mask.
@@ -155,7 +198,7 @@ k_composite(const uint2* __restrict__ ranges, const uint32_t* __restrict__ vals,
         const float bb = B * B;
         const float det = fmaf(A, Cc, -bb) + fmaf(-B, B, bb);
         const float r2 = 2.0f * 0.6931471805599453f * (8.0f + __log2f(q2.y)) * 1.002f + 0.004f;
-        uint32_t m = 0xffu;
+        m = (1u << (kSubCols * kSubRows)) - 1u;
         // not a bounded ellipse as stored (or NaN): evaluate everywhere
         if (cullMode != 0 && det > 0.0f && A > 0.0f && r2 == r2 && fabsf(q0.x) < 1e30f && fabsf(q0.y) < 1e30f)
         {
@@ -209,10 +252,22 @@ k_composite(const uint2* __restrict__ ranges, const uint32_t* __restrict__ vals,
                 }
             }
         }
-        s.mask[buf][sidx] = m;
+        }
+        // transpose the 32 entry masks of this warp's group into one hit word per evaluating warp: the walk below then reads
+        // ONE word per group instead of balloting 32 masks in each of the 8 warps.  Slot k of the group was staged by lane
+        // k ^ 31, hence the bit reversal.
+        uint32_t mine = 0u;
+#pragma unroll
+        for (int wq = 0; wq < kSubCols * kSubRows; wq++)
+        {
+            const uint32_t word = __ballot_sync(0xffffffffu, (m >> wq) & 1u);
+            if (lane == wq) mine = word;
+        }
+        if (lane < kSubCols * kSubRows) s.hits[buf][warp][lane] = __brev(mine);
     };
 
-    const uint32_t warpBit = 1u << warp;
+    const f32x2 pu2 = bcast2(pu);
+    const float kDiscard = 1.0f / 256.0f;
     uint32_t hi = range.y;
     if (hi > range.x) fetch(hi);
     int buf = 0;
@@ -221,24 +276,24 @@ k_composite(const uint2* __restrict__ ranges, const uint32_t* __restrict__ vals,
         const uint32_t cnt = min((uint32_t)kCompChunk, hi - range.x);
         stage(buf);
         // one barrier per chunk: publishes the staged chunk and tells whether every pixel of the tile is finished
-        if (__syncthreads_and(T == 0.0f)) break;
+        if (__syncthreads_and(!live())) break;
         hi -= cnt;
         if (hi > range.x) fetch(hi);
 
-        if (__any_sync(0xffffffffu, T != 0.0f))
+        if (__any_sync(0xffffffffu, live()))
         {
             // 32-bit shared addresses, advanced per group of 32 entries (keeps the walk out of 64-bit address math)
-            uint32_t maskAddr = (uint32_t)__cvta_generic_to_shared(&s.mask[buf][lane]);
+            uint32_t hitAddr = (uint32_t)__cvta_generic_to_shared(&s.hits[buf][0][warp]);
             uint32_t groupAddr = (uint32_t)__cvta_generic_to_shared(&s.a[buf][0]);
-            const uint32_t maskEnd = maskAddr + cnt * 4u;
-            for (; maskAddr < maskEnd; maskAddr += 32 * 4, groupAddr += 32 * 16)
+            const uint32_t hitEnd = hitAddr + ((cnt + 31u) >> 5) * 32u;
+            for (; hitAddr < hitEnd; hitAddr += 32, groupAddr += 32 * 16)
             {
-                uint32_t m;  // slots past the list's end hold 0
-                asm volatile("ld.shared.u32 %0, [%1];" : "=r"(m) : "r"(maskAddr));
-                uint32_t hits = __ballot_sync(0xffffffffu, (m & warpBit) != 0u);
+                uint32_t hits;  // slots past the list's end hold 0
+                asm volatile("ld.shared.u32 %0, [%1];" : "=r"(hits) : "r"(hitAddr));
                 while (hits)
                 {
-                    // 21-instruction body: FLO, BMSK, LOP3, LEA for the walk; 3 LDS; 13 FP32/MUFU; BRA
+                    // hit body, two pixels per thread: FLO, BMSK, LOP3, LEA for the walk; 3 LDS; 5 FFMA2 (log2 w of both pixels),
+                    // 2 MUFU.EX2, 2 FSETP + 2 FSEL (discard), FMUL2, 3 FFMA2, FADD2; BRA
                     uint32_t top, below;
                     asm("bfind.u32 %0, %1;" : "=r"(top) : "r"(hits));                       // index of the highest set bit
                     asm("bmsk.clamp.b32 %0, %1, %2;" : "=r"(below) : "r"(0), "r"(top));   // bits [0, top)
@@ -251,30 +306,48 @@ k_composite(const uint2* __restrict__ ranges, const uint32_t* __restrict__ vals,
                                  : "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w)
                                  : "r"(addr), "n"(sizeof(CompSmem::a)));
                     asm volatile("ld.shared.f32 %0, [%1+%2];" : "=f"(blue) : "r"(addr), "n"(sizeof(CompSmem::a) + sizeof(CompSmem::b)));
-                    const float pw = fmaf(b.y, pvv, fmaf(b.x, puv, fmaf(a.w, puu, fmaf(a.z, pv, fmaf(a.y, pu, a.x)))));
-                    const float w = ex2_approx(pw);
-                    const float tw = (w > (1.0f / 256.0f)) ? T * w : 0.0f;  // discard iff w <= 1/256 (splat_frag.glsl:38)
-                    cr = fmaf(tw, b.z, cr);
-                    cg = fmaf(tw, b.w, cg);
-                    cb = fmaf(tw, blue, cb);
-                    T = T - tw;
+                    // log2 w = c0 + u (c1 + hA u + hB v) + v (c2 + hC v)
+                    f32x2 t1 = fma2(bcast2(b.x), pv, bcast2(a.y));
+                    t1 = fma2(bcast2(a.w), pu2, t1);
+                    const f32x2 t2 = fma2(bcast2(b.y), pv, bcast2(a.z));
+                    f32x2 pw = fma2(pu2, t1, bcast2(a.x));
+                    pw = fma2(pv, t2, pw);
+                    float pw0, pw1;
+                    unpack2(pw, pw0, pw1);
+                    float w0 = ex2_approx(pw0), w1 = ex2_approx(pw1);
+                    w0 = (w0 > kDiscard) ? w0 : 0.0f;  // discard iff w <= 1/256 (splat_frag.glsl:38)
+                    w1 = (w1 > kDiscard) ? w1 : 0.0f;
+                    const f32x2 tw = mul2(T, pack2(w0, w1));
+                    cr = fma2(bcast2(b.z), tw, cr);
+                    cg = fma2(bcast2(b.w), tw, cg);
+                    cb = fma2(bcast2(blue), tw, cb);
+                    T = sub2(T, tw);
                 }
                 // transmittance early-out, checked once per 32 list entries (T only decreases)
-                if (T < earlyOutT) T = 0.0f;
-                // every pixel of this warp finished: leave the rest of the chunk (its hits would all be multiplied by
-                // T = 0).  benchmarks/earlyout_model.py: a fifth of the kernel's hit-loop trips were such trips.
-                if (!__any_sync(0xffffffffu, T != 0.0f)) break;
+                {
+                    float t0, t1;
+                    unpack2(T, t0, t1);
+                    if (t0 < earlyOutT) t0 = 0.0f;
+                    if (t1 < earlyOutT) t1 = 0.0f;
+                    T = pack2(t0, t1);
+                    // every pixel of this warp finished: leave the rest of the chunk (its hits would all be multiplied by
+                    // T = 0).  benchmarks/earlyout_model.py: a fifth of the kernel's hit-loop trips were such trips.
+                    if (!__any_sync(0xffffffffu, t0 != 0.0f || t1 != 0.0f)) break;
+                }
             }
         }
         buf ^= 1;
     }
 
-    if (inside)
-    {
-        const size_t pix = (size_t)y * width + x;
+    float r0, r1, g0, g1, b0, b1;
+    unpack2(cr, r0, r1);
+    unpack2(cg, g0, g1);
+    unpack2(cb, b0, b1);
+    auto store = [&](int yy, float r, float g, float b) {
+        const size_t pix = (size_t)yy * width + x;
         if (HALF)
         {
-            __half2 lo = __floats2half2_rn(cr, cg), hi2 = __floats2half2_rn(cb, 1.0f);
+            __half2 lo = __floats2half2_rn(r, g), hi2 = __floats2half2_rn(b, 1.0f);
             uint2 v;
             v.x = *reinterpret_cast<uint32_t*>(&lo);
             v.y = *reinterpret_cast<uint32_t*>(&hi2);
@@ -282,9 +355,11 @@ k_composite(const uint2* __restrict__ ranges, const uint32_t* __restrict__ vals,
         }
         else
         {
-            reinterpret_cast<float4*>(fb)[pix] = make_float4(cr, cg, cb, 1.0f);
+            reinterpret_cast<float4*>(fb)[pix] = make_float4(r, g, b, 1.0f);
         }
-    }
+    };
+    if (inside0) store(y0, r0, g0, b0);
+    if (inside1) store(y1, r1, g1, b1);
 }
 
 // ---------------------------------------------------------------------------------------------------

@@ -9,8 +9,10 @@ namespace splat
 // ---------------------------------------------------------------------------------------------------
 // pipeline geometry
 // ---------------------------------------------------------------------------------------------------
-constexpr int kTileSize = 16;        // composite tile = 16x16 pixels
-constexpr int kTileShift = 4;
+// composite tile = 32 x 16 pixels: one CTA of 8 warps, each warp an 8x8 pixel block, TWO pixels per thread (packed f32x2
+// arithmetic, composite.cu).  Wider tiles also mean fewer (gaussian, tile) instances to emit, sort and stage.
+constexpr int kTileW = 32, kTileH = 16;
+constexpr int kTileShiftX = 5, kTileShiftY = 4;
 constexpr int kDepthBits = 32;       // low half of the sort key: the reference's u32 depth key
 constexpr int kRadixBits = 8;
 constexpr int kRadixSize = 1 << kRadixBits;

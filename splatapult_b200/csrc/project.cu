@@ -261,8 +261,8 @@ __device__ __forceinline__ Projected project_gaussian(const PackedCloud& cloud, 
                     const float fy0 = fmaxf(ceilf(py - ey - 0.5f), 0.0f), fy1 = fminf(floorf(py + ey - 0.5f), (float)(fc.height - 1));
                     if (fx1 >= fx0 && fy1 >= fy0)  // false for NaN too
                     {
-                        const uint32_t tx0 = (uint32_t)fx0 >> kTileShift, tx1 = (uint32_t)fx1 >> kTileShift;
-                        const uint32_t ty0 = (uint32_t)fy0 >> kTileShift, ty1 = (uint32_t)fy1 >> kTileShift;
+                        const uint32_t tx0 = (uint32_t)fx0 >> kTileShiftX, tx1 = (uint32_t)fx1 >> kTileShiftX;
+                        const uint32_t ty0 = (uint32_t)fy0 >> kTileShiftY, ty1 = (uint32_t)fy1 >> kTileShiftY;
                         const uint32_t w = tx1 - tx0 + 1, h = ty1 - ty0 + 1;
                         count = w * h;
                         rx0 = tx0; ry0 = ty0; rw = w; rh = h;

@@ -432,8 +432,8 @@ struct RendererImpl
         if (vp[0] != 0.0f || vp[1] != 0.0f) return fail(SPL_ERR_ARG, "viewport origin must be (0,0) (the reference assumes it, SURVEY q6)");
         const int W = (int)vp[2], H = (int)vp[3];
         if (W <= 0 || H <= 0 || (float)W != vp[2] || (float)H != vp[3]) return fail(SPL_ERR_ARG, "viewport width/height must be positive integers");
-        const int tilesX = (W + kTileSize - 1) / kTileSize, tilesY = (H + kTileSize - 1) / kTileSize;
-        if (tilesX > 1024 || tilesY > 1024) return fail(SPL_ERR_ARG, "viewport larger than 16384 pixels");
+        const int tilesX = (W + kTileW - 1) / kTileW, tilesY = (H + kTileH - 1) / kTileH;
+        if (tilesX > 1024 || tilesY > 1024) return fail(SPL_ERR_ARG, "viewport larger than 32768 x 16384 pixels");
 
         // frame constants, computed as the reference's CPU side does (float, glm operation order)
         const mat4 camera = mat4::from(cam), projM = mat4::from(proj);
@@ -788,7 +788,7 @@ struct RendererImpl
         out->num_instances = c.totalInstances;
         out->instance_capacity = capacity;
         out->overflow = c.overflow;
-        out->tiles_x = fc.tilesX; out->tiles_y = fc.tilesY; out->tile_size = kTileSize;
+        out->tiles_x = fc.tilesX; out->tiles_y = fc.tilesY; out->tile_w = kTileW; out->tile_h = kTileH;
         out->sort_passes = frameSortMode == SPL_SORT_BINNED ? 1 : sortPasses;  // LSD: 4 depth-digit passes + tile-digit passes
         out->sort_bits = sortBits;
         out->sort_mode = frameSortMode;

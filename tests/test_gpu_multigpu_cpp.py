@@ -39,7 +39,7 @@ def _run(consumer, splat, scratch, nranks, deg):
     proj.astype(np.float32).tofile(projfile)
     r = subprocess.run([consumer, ply, js, prefix, str(nranks), str(W), str(H), projfile], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stdout + r.stderr
-    assert r.stdout.strip().startswith(f"multigpu ok {nranks} ranks"), r.stdout
+    assert any(l.startswith(f"multigpu ok {nranks} ranks") for l in r.stdout.splitlines()), r.stdout  # NCCL may print its version first
     # the same views through the single-GPU path of the C ABI
     gc = splat.GaussianCloud()
     assert gc.ImportPly(ply)

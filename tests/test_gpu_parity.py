@@ -84,11 +84,11 @@ def _check_tile_lists(r, want_rec, want_order, w, h):
             assert np.all(tiles[b:e] == t)
             total += e - b
     assert total == len(keys)
-    assert st.tiles_x == (w + 15) // 16 and st.tiles_y == (h + 15) // 16
+    assert st.tiles_x == (w + st.tile_w - 1) // st.tile_w and st.tiles_y == (h + st.tile_h - 1) // st.tile_h
     return tiles, vals
 
 
-def _coverage_is_conservative(want_rec, tiles, vals, w, h, tiles_x):
+def _coverage_is_conservative(want_rec, tiles, vals, w, h, tiles_x, tile_w=32, tile_h=16):
     """every pixel the oracle's fragment test accepts lies in a tile instanced for that gaussian."""
     inst = set(zip(vals.tolist(), tiles.tolist()))
     ys, xs = np.mgrid[0:h, 0:w]
@@ -98,7 +98,7 @@ def _coverage_is_conservative(want_rec, tiles, vals, w, h, tiles_x):
         dx, dy = (fx - s["px"]).astype(np.float32), (fy - s["py"]).astype(np.float32)
         q = dx * (s["i00"] * dx + s["i10"] * dy) + dy * (s["i01"] * dx + s["i11"] * dy)
         hit = s["alpha"] * np.exp(-0.5 * q) > 1 / 256
-        for t in np.unique((ys[hit] // 16) * tiles_x + xs[hit] // 16):
+        for t in np.unique((ys[hit] // tile_h) * tiles_x + xs[hit] // tile_w):
             assert (int(i), int(t)) in inst, (i, t)
 
 
@@ -125,7 +125,7 @@ def test_reference_fixture_config1(splat, oracle, golden_dir):
     fb = _frame(r, g["camera"], g["proj"], 640, 480)
     _check_records(r.Tap(api.TAP_RECORDS), g["records"])
     tiles, vals = _check_tile_lists(r, g["records"], g["order"], 640, 480)
-    _coverage_is_conservative(g["records"], tiles, vals, 640, 480, 40)
+    _coverage_is_conservative(g["records"], tiles, vals, 640, 480, r.GetStats().tiles_x)
     _check_image(fb, g["fb"])
     st = r.GetStats()
     assert st.num_visible == 16 and st.sh_mode == 3 and st.kernel_launches >= 5
@@ -140,7 +140,7 @@ def test_golden_synth_deg3(splat, golden_dir):
     fb = _frame(r, g["camera"], g["proj"], 320, 180)
     _check_records(r.Tap(api.TAP_RECORDS), g["records"])
     tiles, vals = _check_tile_lists(r, g["records"], g["order"], 320, 180)
-    _coverage_is_conservative(g["records"], tiles, vals, 320, 180, 20)
+    _coverage_is_conservative(g["records"], tiles, vals, 320, 180, r.GetStats().tiles_x)
     _check_image(fb, g["fb"])
 
 

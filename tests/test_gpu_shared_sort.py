@@ -86,7 +86,7 @@ def test_second_eye_in_the_first_eyes_order(splat, oracle, scratch, deg):
     _check_image(fb_right, oracle.composite(rec, order, W, H), exact_mode=True)
     # the second eye cost one projection, one expansion, the tile-digit passes and the composite: no depth passes
     st = r.GetStats()
-    tiles = ((W + 15) // 16) * ((H + 15) // 16)
+    tiles = int(st.tiles_x * st.tiles_y)
     tile_passes = (max(tiles - 1, 1).bit_length() + 7) // 8
     assert st.kernel_launches == 2 + tile_passes + 1, st.kernel_launches
     # the test discriminates: the exact order for the right eye is a different one
@@ -157,7 +157,10 @@ def test_overflow_in_the_second_eye_is_redone(splat, oracle, scratch):
     left, right = scenes.translate(-0.03, 0, 4), scenes.look_at_camera((0.03, 0.0, 4.0), (-0.2, 0.0, 0.0))
     r.Sort(left, proj, vp, NF)
     r.Render(left, proj, vp, NF)
-    r.Render(right, proj, vp, NF)
+    try:
+        r.Render(right, proj, vp, NF)
+    except splat.SplatError as e:  # the left eye's frame has already reported that it was incomplete (a notification:
+        assert e.code == -4        # the Render itself was carried out)
     assert r.GetStats().overflow
     fb = r.ReadFramebuffer()  # grows, sorts for the left eye again, re-projects for the right one
     assert not r.GetStats().overflow
