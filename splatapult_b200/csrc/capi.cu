@@ -318,6 +318,8 @@ struct spl_sorter
     uint64_t capacity = 0;
     void* control = nullptr;  // n | tickets | histograms
     unsigned long long* status = nullptr;
+    unsigned long long* groups = nullptr;  // group aggregates of the look-back, zeroed per sort
+    size_t groupWordsPerPass = 0;
     uint32_t generation = 0;
     int keysPerThread = 16;
 };
@@ -344,12 +346,15 @@ spl_sorter* spl_sorter_create(int device, uint64_t capacity)
     s->capacity = capacity < (uint64_t)splat::kSortTileKeys ? splat::kSortTileKeys : capacity;
     cudaDeviceProp prop{};
     if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) s->numSMs = prop.multiProcessorCount;
+    s->groupWordsPerPass = splat::sort_group_words(s->capacity, s->keysPerThread);
     if (cudaMalloc(&s->control, kSorterControlBytes) != cudaSuccess ||
-        cudaMalloc(&s->status, splat::sort_status_bytes(s->capacity, splat::kMaxSortPasses)) != cudaSuccess)
+        cudaMalloc(&s->status, splat::sort_status_bytes(s->capacity, splat::kMaxSortPasses)) != cudaSuccess ||
+        cudaMalloc(&s->groups, splat::kMaxSortPasses * s->groupWordsPerPass * sizeof(unsigned long long)) != cudaSuccess)
     {
         set_error(SPL_ERR_ALLOC, "cudaMalloc failed");
         cudaFree(s->control);
         cudaFree(s->status);
+        cudaFree(s->groups);
         delete s;
         return nullptr;
     }
@@ -362,6 +367,7 @@ void spl_sorter_destroy(spl_sorter* s)
     cudaSetDevice(s->device);
     cudaFree(s->control);
     cudaFree(s->status);
+    cudaFree(s->groups);
     delete s;
 }
 
@@ -384,6 +390,9 @@ int spl_sorter_sort(spl_sorter* s, void* d_keys_in, void* d_vals_in, void* d_key
         ++s->generation;
     }
     splat::SortWorkspace ws{ctl + 64, s->status, ctl + 8, s->capacity, s->generation, s->keysPerThread, 0};
+    SORTER_TRY(cudaMemsetAsync(s->groups, 0, (size_t)passes * s->groupWordsPerPass * sizeof(unsigned long long), stream));
+    ws.groupAgg = s->groups;
+    ws.groupWordsPerPass = s->groupWordsPerPass;
     auto* kin = static_cast<unsigned long long*>(d_keys_in);
     auto* kout = static_cast<unsigned long long*>(d_keys_out);
     auto* vin = static_cast<uint32_t*>(d_vals_in);

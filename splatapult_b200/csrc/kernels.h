@@ -18,6 +18,7 @@ cudaError_t pack_cloud(const void* deviceAos, uint32_t n, uint32_t strideBytes, 
 // ---- project.cu
 uint32_t project_num_blocks(uint32_t n);
 // digit0Hist: 256 global counters that receive the histogram of the emitted keys' lowest digit (may be null)
+// (launch_project_keys: 4 x 256 counters, the histograms of all four depth digits)
 cudaError_t launch_project(const PackedCloud& cloud, const FrameConstants& fc, ProjRecord* rec, unsigned long long* keys, uint32_t* vals,
                            FrameCounters* ctr, unsigned long long* scanState, uint32_t capacity, uint32_t* digit0Hist, cudaStream_t stream);
 
@@ -59,7 +60,15 @@ struct SortWorkspace
     // (so an untouched tile reads as begin = 0xFFFFFFFF, end = 0: empty); updated with atomicMax.
     uint2* tileRanges = nullptr;
     uint32_t numRangeTiles = 0;
+    // the producer left the histograms of EVERY digit of this sort (k_project_keys does for the four depth digits): no pass
+    // accumulates the next digit's histogram
+    bool allHistogramsReady = false;
+    // optional group aggregates of the look-back (radix_sort.cu): pass p uses words [p * groupWordsPerPass, ...), each pass
+    // needs sort_group_words(keys it may see, keysPerThread) 64-bit words, ZEROED by the caller before every sort
+    unsigned long long* groupAgg = nullptr;
+    size_t groupWordsPerPass = 0;
 };
+size_t sort_group_words(uint64_t capacity, int keysPerThread);
 constexpr uint32_t kFusedRangeBeginXor = 0xFFFFFFFFu;  // begin = ranges[t].x ^ this
 size_t sort_status_bytes(uint64_t capacity, int passes);
 // keys/vals ping-pong between (A) and (B); passes = ceil((endBit-beginBit)/8); the sorted result is in A when

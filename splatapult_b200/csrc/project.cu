@@ -632,9 +632,12 @@ k_project_keys(const PackedCloud cloud, const __grid_constant__ FrameConstants f
     // grid-stride over chunks of 256 gaussians: the CTA keeps its digit histogram and its visible count across chunks
     // and flushes them once.  (With one CTA per chunk and one atomicAdd per warp on ctr->visible, that single L2
     // address took N/32 serialised atomics: the kernel's time was their time -- 58 us at 1 M, 553 us at 6 M gaussians.)
-    __shared__ uint32_t sDigit0[kRadixSize];
+    // histograms of ALL FOUR depth digits: the keys are in registers here, so the depth passes of the sorter neither need a
+    // histogram pass nor accumulate the next digit's histogram while they scatter
+    __shared__ uint32_t sDigit[kDepthBits / kRadixBits][kRadixSize];
     const int tid = threadIdx.x;
-    sDigit0[tid] = 0;
+#pragma unroll
+    for (int p = 0; p < kDepthBits / kRadixBits; p++) sDigit[p][tid] = 0;
     __syncthreads();
     uint32_t visibleMine = 0;
     const uint32_t numChunks = (cloud.n + kProjThreads - 1) / kProjThreads;
@@ -653,7 +656,8 @@ k_project_keys(const PackedCloud cloud, const __grid_constant__ FrameConstants f
                 const uint32_t key = sorted ? pg.refKey : 0xFFFFFFFFu;
                 keys[i] = key;
                 vals[i] = i;
-                smem_red_add(&sDigit0[key & (kRadixSize - 1)], 1u);
+#pragma unroll
+                for (int p = 0; p < kDepthBits / kRadixBits; p++) smem_red_add(&sDigit[p][(key >> (p * kRadixBits)) & (kRadixSize - 1)], 1u);
             }
         }
         visibleMine += pg.visible ? 1u : 0u;
@@ -668,8 +672,12 @@ k_project_keys(const PackedCloud cloud, const __grid_constant__ FrameConstants f
     if ((tid & 31) == 0 && visibleMine) atomicAdd(&sVisible, visibleMine);
     __syncthreads();
     if (tid == 0 && sVisible) atomicAdd(&ctr->visible, sVisible);
-    const uint32_t c = sDigit0[tid];
-    if (c) atomicAdd(digit0Hist + tid, c);  // all zero in a render-only pass
+#pragma unroll
+    for (int p = 0; p < kDepthBits / kRadixBits; p++)
+    {
+        const uint32_t c = sDigit[p][tid];
+        if (c) atomicAdd(digit0Hist + p * kRadixSize + tid, c);  // all zero in a render-only pass
+    }
 }
 
 // ---------------------------------------------------------------------------------------------------

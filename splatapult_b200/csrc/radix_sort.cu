@@ -57,6 +57,18 @@ __device__ __forceinline__ uint32_t st_pack(uint32_t flag, uint32_t gen, uint32_
 }
 __device__ __forceinline__ bool st_valid(uint32_t w, uint32_t gen) { return (w >> 30) != 0 && ((w >> 24) & kSortGenerationMask) == (gen & kSortGenerationMask); }
 
+// Group aggregates.  With all tiles of a pass resident at once (1 M keys = 245 tiles = one wave) nobody has a prefix when the
+// walks start, so tile t used to sum t predecessor rows: O(tiles^2) L2 reads and ~30 dependent round trips per tile.  Every
+// kLookGroup consecutive tiles therefore also add their digit counts into ONE 64-bit word per (group, digit):
+//   groupAgg[group][digit] += (1 << kGroupArrivalShift) | count          (a single RED.64: arrivals and sum move together,
+//                                                                         so no fence or separate "done" counter is needed)
+// A walker sums the status words of its own group's predecessors (at most kLookGroup - 1), then one word per earlier group,
+// short-cutting as soon as the last tile of a group has published its inclusive prefix.  The words are zeroed per sort by
+// the owner of the workspace (they accumulate, so they cannot carry a generation).
+constexpr int kLookGroup = 16;
+constexpr int kGroupArrivalShift = 40;
+constexpr unsigned long long kGroupCountMask = (1ull << kGroupArrivalShift) - 1ull;
+
 // ---------------------------------------------------------------------------------------------------
 // S1 (stand-alone sorter only): histogram of the FIRST digit; TMA-staged, double-buffered
 // ---------------------------------------------------------------------------------------------------
@@ -163,7 +175,7 @@ k_sort_onesweep(const KeyT* __restrict__ keysIn, const uint32_t* __restrict__ va
                 uint32_t* __restrict__ valsOut, const uint32_t* __restrict__ nDevice, int shift, uint32_t mask, int nextShift, uint32_t nextMask,
                 const uint32_t* __restrict__ histogram, uint32_t* __restrict__ histogramNext, unsigned long long* __restrict__ status,
                 uint32_t* __restrict__ ticket, uint32_t gen, unsigned long long* tl, uint2* __restrict__ tileRanges, uint32_t numRangeTiles,
-                uint32_t statusTiles, int rangeShift)
+                uint32_t statusTiles, int rangeShift, unsigned long long* __restrict__ groupAgg)
 {
     using Smem = SortSmem<KPT, KeyT>;
     constexpr int kTile = Smem::kTile;
@@ -322,6 +334,7 @@ k_sort_onesweep(const KeyT* __restrict__ keysIn, const uint32_t* __restrict__ va
             const uint32_t cnt = run;
             uint32_t* myLo = statusLo + (size_t)tile * kRadixSize + tid;
             uint32_t* myHi = statusHi + (size_t)tile * kRadixSize + tid;
+            const uint32_t grp = tile / kLookGroup;
             if (digitUsed)
             {
                 if (tile == 0)
@@ -332,6 +345,8 @@ k_sort_onesweep(const KeyT* __restrict__ keysIn, const uint32_t* __restrict__ va
                 {
                     st_relaxed_u32(myLo, st_pack(kStAggregate, gen, cnt));
                 }
+                // arrival + count into the group's word (result unused: compiles to RED.64); also when cnt == 0
+                if (groupAgg) atomicAdd(groupAgg + (size_t)grp * kRadixSize + tid, (1ull << kGroupArrivalShift) | (unsigned long long)cnt);
             }
 
             uint32_t incl = cnt;
@@ -355,6 +370,8 @@ k_sort_onesweep(const KeyT* __restrict__ keysIn, const uint32_t* __restrict__ va
                 // windowed look-back: kLookWindow predecessors are polled with independent loads in flight, so
                 // the walk costs one L2 round trip per window instead of one per tile
                 constexpr int kLookWindow = 8;
+                // phase 1: the predecessors inside this tile's own group (all of them when there are no group aggregates)
+                const int floorTile = groupAgg ? (int)(grp * kLookGroup) : 0;
                 int t = (int)tile - 1;
                 bool done = false, hasHi = false;
                 while (!done)
@@ -362,7 +379,7 @@ k_sort_onesweep(const KeyT* __restrict__ keysIn, const uint32_t* __restrict__ va
                     uint32_t v[kLookWindow];
 #pragma unroll
                     for (int i = 0; i < kLookWindow; i++)
-                        v[i] = (t - i >= 0) ? ld_relaxed_u32(statusLo + (size_t)(t - i) * kRadixSize + tid) : st_pack(kStPrefix, gen, 0u);
+                        v[i] = (t - i >= floorTile) ? ld_relaxed_u32(statusLo + (size_t)(t - i) * kRadixSize + tid) : st_pack(kStPrefix, gen, 0u);
                     int used = 0;
 #pragma unroll
                     for (int i = 0; i < kLookWindow; i++)
@@ -380,12 +397,60 @@ k_sort_onesweep(const KeyT* __restrict__ keysIn, const uint32_t* __restrict__ va
                     }
                     t -= used;  // re-poll from the first word that was not yet published
                 }
-                // the walk ended on the prefix word of tile t + 1; if that prefix did not fit 24 bits its publisher stored
-                // hi, then lo with release: re-read lo with acquire, then hi
+                int prefixTile = t + 1;  // the walk ended on the prefix word of this tile (floorTile - 1: the virtual one)
+                if (prefixTile < floorTile && floorTile > 0)
+                {
+                    // phase 2: one word per earlier group (all of them complete groups of kLookGroup tiles), newest first;
+                    // the inclusive prefix of a group's LAST tile, once published, ends the walk
+                    constexpr int kGroupWindow = 4;
+                    int gg = (int)grp - 1;
+                    done = false;
+                    hasHi = false;
+                    while (!done)
+                    {
+                        unsigned long long a[kGroupWindow];
+                        uint32_t p[kGroupWindow];
+#pragma unroll
+                        for (int i = 0; i < kGroupWindow; i++)
+                        {
+                            const int gi = gg - i;
+                            a[i] = gi >= 0 ? ld_relaxed_u64(groupAgg + (size_t)gi * kRadixSize + tid) : 0ull;
+                            p[i] = gi >= 0 ? ld_relaxed_u32(statusLo + ((size_t)gi * kLookGroup + (kLookGroup - 1)) * kRadixSize + tid) : 0u;
+                        }
+                        int used = 0;
+#pragma unroll
+                        for (int i = 0; i < kGroupWindow; i++)
+                        {
+                            if (!done && used == i)
+                            {
+                                const int gi = gg - i;
+                                if (gi < 0)
+                                {
+                                    done = true;  // before group 0: prefix 0
+                                }
+                                else if (st_valid(p[i], gen) && (p[i] >> 30) == 2)
+                                {
+                                    prior += p[i] & kStCountMask;
+                                    hasHi = (p[i] & kStHasHi) != 0u;
+                                    prefixTile = gi * kLookGroup + (kLookGroup - 1);
+                                    done = true;
+                                }
+                                else if ((a[i] >> kGroupArrivalShift) == (unsigned long long)kLookGroup)
+                                {
+                                    prior += (uint32_t)(a[i] & kGroupCountMask);
+                                    used = i + 1;
+                                }
+                            }
+                        }
+                        gg -= used;  // re-poll from the first group that was not yet complete
+                    }
+                }
+                // if the prefix the walk ended on did not fit 24 bits its publisher stored hi, then lo with release: re-read lo
+                // with acquire, then hi
                 if (hasHi)
                 {
-                    (void)ld_acquire_u32(statusLo + (size_t)(t + 1) * kRadixSize + tid);
-                    prior += ld_relaxed_u32(statusHi + (size_t)(t + 1) * kRadixSize + tid) << 24;
+                    (void)ld_acquire_u32(statusLo + (size_t)prefixTile * kRadixSize + tid);
+                    prior += ld_relaxed_u32(statusHi + (size_t)prefixTile * kRadixSize + tid) << 24;
                 }
                 const uint32_t total = prior + cnt;
                 if (total > kStCountMask)
@@ -460,6 +525,13 @@ k_sort_onesweep(const KeyT* __restrict__ keysIn, const uint32_t* __restrict__ va
     }
 }
 
+size_t sort_group_words(uint64_t capacity, int keysPerThread)
+{
+    const uint64_t tileKeys = (uint64_t)kSortThreads * (keysPerThread == 8 ? 8 : 16);
+    const uint64_t tiles = (capacity + tileKeys - 1) / tileKeys;
+    return (size_t)((tiles + kLookGroup - 1) / kLookGroup + 1) * kRadixSize;
+}
+
 size_t sort_status_bytes(uint64_t capacity, int passes)
 {
     const uint64_t maxTiles = (capacity + kSortMinTileKeys - 1) / kSortMinTileKeys + 1;
@@ -504,13 +576,14 @@ static cudaError_t launch_passes_t(KeyT* keysA, uint32_t* valsA, KeyT* keysB, ui
         uint32_t* vout = (p & 1) ? valsA : valsB;
         const int shift = beginBit + p * kRadixBits;
         const bool last = p == passes - 1;
+        const bool wantNext = !last && !ws.allHistogramsReady;
         const int nshift = last ? 0 : shift + kRadixBits;
         k_sort_onesweep<KPT, KeyT><<<grid, kSortThreads, sizeof(Smem), stream>>>(
             kin, vin, kout, vout, nDevice, shift, digit_mask(shift, endBit), nshift, last ? 0u : digit_mask(nshift, endBit),
-            ws.histograms + (ws.passOffset + p) * kRadixSize, last ? nullptr : ws.histograms + (ws.passOffset + p + 1) * kRadixSize,
+            ws.histograms + (ws.passOffset + p) * kRadixSize, wantNext ? ws.histograms + (ws.passOffset + p + 1) * kRadixSize : nullptr,
             ws.status + (size_t)(ws.passOffset + p) * maxTiles * kRadixSize, ws.tickets + ws.passOffset + p, ws.generation, dTl ? dTl + p * tlWords : nullptr,
             last && shift >= kRangeShift ? ws.tileRanges : nullptr, ws.numRangeTiles,  // the digit must be part of the tile id
-            (uint32_t)maxTiles, kRangeShift);
+            (uint32_t)maxTiles, kRangeShift, ws.groupAgg ? ws.groupAgg + (size_t)p * ws.groupWordsPerPass : nullptr);
     }
 #ifdef SPL_SORT_TIMELINE
     if (tlPath)

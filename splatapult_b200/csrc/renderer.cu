@@ -70,7 +70,9 @@ struct RendererImpl
     unsigned long long *dKeysA = nullptr, *dKeysB = nullptr;
     uint32_t *dValsA = nullptr, *dValsB = nullptr;
     void* dControl = nullptr;
-    size_t controlBytes = 0;
+    size_t controlBytes = 0;           // fixed part: counters | histograms | scan state | tile ranges (cleared every frame)
+    size_t controlAllocBytes = 0;      // + the sorter's group-aggregate words, of which a frame clears only what its passes use
+    unsigned long long* dGroups = nullptr;  // inside dControl, right after the fixed part
     FrameCounters* dCtr = nullptr;
     uint32_t* dHist = nullptr;
     unsigned long long* dScan = nullptr;
@@ -250,6 +252,7 @@ struct RendererImpl
         CU_TRY(cudaMemsetAsync(dValsA, 0, padded * 4, stream));
         CU_TRY(cudaMemsetAsync(dValsB, 0, padded * 4, stream));
         capacity = want;
+        if (dControl) return allocControl(rangesTiles);  // the group-aggregate words are sized by the capacity
         return ok();
     }
 
@@ -261,15 +264,26 @@ struct RendererImpl
         dControl = nullptr;
         const size_t scanBytes = (size_t)std::max<uint32_t>(project_num_blocks(n), 1) * sizeof(unsigned long long);
         const size_t histBytes = kMaxSortPasses * kRadixSize * sizeof(uint32_t);
-        controlBytes = 256 + histBytes + scanBytes + (size_t)tiles * sizeof(uint2);
-        CU_TRY(cudaMalloc(&dControl, controlBytes));
+        controlBytes = (256 + histBytes + scanBytes + (size_t)tiles * sizeof(uint2) + 15) & ~(size_t)15;
+        // group aggregates: four depth passes over at most n keys, then the instance passes over at most `capacity` keys
+        // (sized for the small sort tile, 8 keys per thread: SPL_OPT_SORT_TILE may change after Init)
+        const size_t groupWords = 4 * sort_group_words(std::max<uint32_t>(n, 1), 8) + (size_t)kMaxSortPasses * sort_group_words(std::max<uint64_t>(capacity, 1), 8);
+        controlAllocBytes = controlBytes + groupWords * sizeof(unsigned long long);
+        CU_TRY(cudaMalloc(&dControl, controlAllocBytes));
         uint8_t* base = static_cast<uint8_t*>(dControl);
         dCtr = reinterpret_cast<FrameCounters*>(base);
         dHist = reinterpret_cast<uint32_t*>(base + 256);
         dScan = reinterpret_cast<unsigned long long*>(base + 256 + histBytes);
         dRanges = reinterpret_cast<uint2*>(base + 256 + histBytes + scanBytes);
-        CU_TRY(cudaMemsetAsync(dControl, 0, controlBytes, stream));
+        dGroups = reinterpret_cast<unsigned long long*>(base + controlBytes);
+        CU_TRY(cudaMemsetAsync(dControl, 0, controlAllocBytes, stream));
         return 0;
+    }
+    // bytes of the control block a frame with `depthPasses` passes over the gaussians and `instPasses` over the instances clears
+    size_t frameControlBytes(int depthPasses, int instPasses) const
+    {
+        return controlBytes + ((size_t)depthPasses * sort_group_words(std::max<uint32_t>(n, 1), sortKpt) +
+                               (size_t)instPasses * sort_group_words(std::max<uint64_t>(capacity, 1), sortKpt)) * sizeof(unsigned long long);
     }
 
     int initFromDevice(const void* dAos, size_t count, size_t stride, bool fullSH, bool srgbIn)
@@ -396,6 +410,8 @@ struct RendererImpl
         if (tilePasses > 0)
         {
             SortWorkspace wsTile{dHist, dStatus, dCtr->sortTickets, capacity, sortGeneration, sortKpt, 4, rangesFused ? dRanges : nullptr, numTiles};
+            wsTile.groupAgg = dGroups + 4 * sort_group_words(std::max<uint32_t>(n, 1), sortKpt);
+            wsTile.groupWordsPerPass = sort_group_words(std::max<uint64_t>(capacity, 1), sortKpt);
             CU_TRY(launch_sort_passes32(keysB32, dValsB, keysA32, dValsA, &dCtr->usedInstances, capacity, 0, tileBits, wsTile, numSMs, stream));
             launches += tilePasses;
             if (tilePasses & 1) { dSortedKeys = dKeysA; dSortedVals = dValsA; }
@@ -475,7 +491,12 @@ struct RendererImpl
         frameSortMode = sortMode;
         rangesFused = false;
         if (profile) CU_TRY(cudaEventRecord(ev[0], stream));
-        CU_TRY(cudaMemsetAsync(dControl, 0, controlBytes, stream));
+        {
+            const int tilePassesNow = (sortBits - kDepthBits + kRadixBits - 1) / kRadixBits;
+            const size_t clearBytes = frameSortMode == SPL_SORT_BINNED ? controlBytes
+                                      : frameSortMode == SPL_SORT_LSD_FLAT ? frameControlBytes(0, sortPasses) : frameControlBytes(4, tilePassesNow);
+            CU_TRY(cudaMemsetAsync(dControl, 0, clearBytes, stream));
+        }
         if (frameSortMode == SPL_SORT_BINNED)
         {
             // MSD by tile: count -> scan (= tile ranges) -> scatter into segments -> per-segment shared-memory sort
@@ -521,6 +542,8 @@ struct RendererImpl
                 if (profile) CU_TRY(cudaEventRecord(ev[1], stream));
                 if (profile) CU_TRY(cudaEventRecord(ev[6], stream));
                 SortWorkspace ws{dHist, dStatus, dCtr->sortTickets, capacity, sortGeneration, sortKpt, 0, rangesFused ? dRanges : nullptr, numTiles};
+                ws.groupAgg = dGroups;
+                ws.groupWordsPerPass = sort_group_words(std::max<uint64_t>(capacity, 1), sortKpt);
                 CU_TRY(launch_sort_passes(dKeysA, dValsA, dKeysB, dValsB, &dCtr->usedInstances, capacity, 0, sortBits, ws, numSMs, stream));
                 launches += sortPasses;
                 sortedKeyBytes = 8;
@@ -544,6 +567,9 @@ struct RendererImpl
                 if (profile) CU_TRY(cudaEventRecord(ev[1], stream));
                 NvtxScope sortZone("sort");
                 SortWorkspace wsDepth{dHist, dStatus, dCtr->sortTickets, capacity, sortGeneration, sortKpt, 0};
+                wsDepth.allHistogramsReady = true;  // k_project_keys left all four depth-digit histograms
+                wsDepth.groupAgg = dGroups;
+                wsDepth.groupWordsPerPass = sort_group_words(std::max<uint32_t>(n, 1), sortKpt);
                 CU_TRY(launch_sort_passes32(keysA32, dValsA, keysB32, dValsB, &dCtr->sortCount, capacity, 0, kDepthBits, wsDepth, numSMs, stream));
                 launches += 4;
                 // 4 passes: the sorted ids are back in dValsA
@@ -592,7 +618,7 @@ struct RendererImpl
         }
         launches = 0;
         if (profile) CU_TRY(cudaEventRecord(ev[0], stream));
-        CU_TRY(cudaMemsetAsync(dControl, 0, controlBytes, stream));  // counters, histograms, scan state, tile ranges
+        CU_TRY(cudaMemsetAsync(dControl, 0, frameControlBytes(4, (sortBits - kDepthBits + kRadixBits - 1) / kRadixBits), stream));  // counters, histograms, scan state, tile ranges, group words
         CU_TRY(launch_project_keys(cloud, fc, dRec, nullptr, nullptr, reinterpret_cast<uint2*>(dSide), dCtr, dHist, stream));
         launches += n ? 1 : 0;
         if (profile) CU_TRY(cudaEventRecord(ev[1], stream));
