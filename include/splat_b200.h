@@ -150,10 +150,14 @@ enum {
     SPL_OPT_EARLY_OUT_T = 0,  /* stop a pixel when its transmittance drops below this (default 1e-4; 0 = exact) */
     SPL_OPT_PROFILE = 1,      /* 1: bracket stages with CUDA events (stage_ms) */
     SPL_OPT_INSTANCES_PER_GAUSSIAN = 2, /* initial capacity factor, before init (default 16) */
-    SPL_OPT_SORT_TILE = 4,    /* keys per onesweep tile: 4096 (default) or 2048 */
+    SPL_OPT_SORT_TILE = 4,    /* keys per onesweep tile: 0 (default) = automatic (2048 for a sort that would not fill one wave of
+                                 CTAs with 4096-key tiles, else 4096), or 2048 / 4096 for every sort of the frame */
     SPL_OPT_SORT_MODE = 3,    /* SPL_SORT_LSD (default), SPL_SORT_LSD_FLAT or SPL_SORT_BINNED; all give bit-identical tile lists */
     SPL_OPT_SUBBLOCK_CULL = 5, /* compositor's per-entry 8x4 sub-block mask: 0 none, 1 footprint box, 2 exact ellipse (default);
                                  culling only skips lanes whose weight is discarded anyway: images are bit-identical */
+    SPL_OPT_PDL = 7,          /* 1 (default): the kernels of a frame are chained as programmatic dependent launches (a kernel's
+                                 prologue overlaps the tail of the one before it; griddepcontrol.wait guards every dependent
+                                 read).  0: plain stream order.  Results are identical. */
     SPL_OPT_SHARED_SORT = 6   /* what a Render does whose arguments differ from the last Sort's (the VR pattern: Sort for
                                  eye 0, Render for both eyes, src/app.cpp:603-607).  0 (default): sort again for the new
                                  view -- every image is exactly ordered.  1: the reference's behaviour -- keep the list and

@@ -19,6 +19,7 @@ OPT_SORT_MODE = 3
 OPT_SORT_TILE = 4
 OPT_SUBBLOCK_CULL = 5
 OPT_SHARED_SORT = 6
+OPT_PDL = 7
 SORT_BINNED = 0
 SORT_LSD = 1
 SORT_LSD_FLAT = 2

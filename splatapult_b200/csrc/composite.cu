@@ -118,6 +118,7 @@ k_composite(const uint2* __restrict__ ranges, const uint32_t* __restrict__ vals,
             void* __restrict__ fb, int width, int height, int tilesX, float earlyOutT, int cullMode, uint32_t beginXor, FrameReport report)
 {
     __shared__ CompSmem s;
+    pdl_wait();  // tile ranges, sorted ids and records are the preceding kernels' output (no-op in a normal launch)
 
     // frame report (renderer.cu: pollReports): the instance count this frame needed, tagged with the frame's sequence number,
     // posted to a word of mapped host memory -- a fire-and-forget PCIe write, so the host learns about a capacity overflow on
@@ -398,15 +399,15 @@ cudaError_t launch_present_rgba8(const void* framebuffer, int fbFormat, uint32_t
 
 cudaError_t launch_composite(const uint2* ranges, const uint32_t* sortedVals, int idStrideWords, const ProjRecord* rec, void* framebuffer,
                              int fbFormat, int width, int height, int tilesX, int tilesY, float earlyOutT, int cullMode, uint32_t rangeBeginXor,
-                             const FrameReport& report, cudaStream_t stream)
+                             const FrameReport& report, cudaStream_t stream, bool pdl)
 {
     const int tiles = tilesX * tilesY;
     if (tiles <= 0) return cudaSuccess;
     if (fbFormat == 1)
-        k_composite<true><<<tiles, kCompThreads, 0, stream>>>(ranges, sortedVals, idStrideWords, rec, framebuffer, width, height, tilesX, earlyOutT, cullMode, rangeBeginXor, report);
-    else
-        k_composite<false><<<tiles, kCompThreads, 0, stream>>>(ranges, sortedVals, idStrideWords, rec, framebuffer, width, height, tilesX, earlyOutT, cullMode, rangeBeginXor, report);
-    return cudaGetLastError();
+        return launch_kernel(k_composite<true>, dim3(tiles), dim3(kCompThreads), 0, stream, pdl, ranges, sortedVals, idStrideWords, rec, framebuffer, width, height, tilesX,
+                             earlyOutT, cullMode, rangeBeginXor, report);
+    return launch_kernel(k_composite<false>, dim3(tiles), dim3(kCompThreads), 0, stream, pdl, ranges, sortedVals, idStrideWords, rec, framebuffer, width, height, tilesX,
+                         earlyOutT, cullMode, rangeBeginXor, report);
 }
 
 }  // namespace splat

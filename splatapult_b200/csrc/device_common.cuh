@@ -186,6 +186,16 @@ __device__ __forceinline__ float sqrt_approx(float x)
     return y;
 }
 
+// Programmatic dependent launch (a kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may start before
+// its predecessor in the stream has finished; both instructions are no-ops in a normally launched kernel):
+//   pdl_wait()    -- returns when the preceding kernel has completed and its memory operations are visible.  Everything a
+//                    kernel reads from ANY earlier kernel of the frame must come after it ...
+//   pdl_trigger() -- ... and is called only AFTER the kernel's own pdl_wait(): the next kernel is launched once every CTA
+//                    of this one has triggered (or exited), so the next kernel's code BEFORE its wait runs after this
+//                    kernel's predecessor has completed, but concurrently with this kernel's tail.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 __device__ __forceinline__ uint32_t lanemask_lt()
 {
     uint32_t m;

@@ -9,6 +9,23 @@
 namespace splat
 {
 
+// kernel launch, optionally as a programmatic dependent of the preceding kernel in the stream (device_common.cuh: pdl_wait)
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_kernel(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, bool pdl, Args&&... args)
+{
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 // ---- pack.cu
 size_t packed_cloud_bytes(uint32_t n, int shMode);
 cudaError_t detect_sh_mode(const void* deviceAos, uint32_t n, uint32_t strideBytes, bool hasFullSH, unsigned int* dFlagScratch,
@@ -27,9 +44,11 @@ cudaError_t launch_project(const PackedCloud& cloud, const FrameConstants& fc, P
 // depth order (scan + coalesced emission) and leave the histogram of the first tile digit in tileDigitHist
 cudaError_t launch_project_keys(const PackedCloud& cloud, const FrameConstants& fc, ProjRecord* rec, uint32_t* keys, uint32_t* vals,
                                 uint2* side, FrameCounters* ctr, uint32_t* digit0Hist, cudaStream_t stream);
+// tileDigitHist: 2 x 256 counters, the histograms of BOTH tile digits (bits 0-7 and 8-15 of the tile id).  pdl: launch as a
+// programmatic dependent of the preceding kernel (the last depth pass)
 cudaError_t launch_emit_sorted(const uint32_t* sortedVals, const uint2* side, uint32_t n,
                                const FrameConstants& fc, uint32_t* keys, uint32_t* vals, FrameCounters* ctr,
-                               unsigned long long* scanState, uint32_t capacity, uint32_t* tileDigitHist, cudaStream_t stream);
+                               unsigned long long* scanState, uint32_t capacity, uint32_t* tileDigitHist, cudaStream_t stream, bool pdl = false);
 
 cudaError_t launch_project_bin(const PackedCloud& cloud, const FrameConstants& fc, ProjRecord* rec, uint4* side, uint32_t* tileCount,
                                FrameCounters* ctr, cudaStream_t stream);
@@ -67,6 +86,9 @@ struct SortWorkspace
     // needs sort_group_words(keys it may see, keysPerThread) 64-bit words, ZEROED by the caller before every sort
     unsigned long long* groupAgg = nullptr;
     size_t groupWordsPerPass = 0;
+    // launch every pass as a programmatic dependent of the kernel before it (device_common.cuh: pdl_wait); the first pass
+    // then assumes that its histogram row comes from that kernel, later passes only when allHistogramsReady is false
+    bool pdl = false;
 };
 size_t sort_group_words(uint64_t capacity, int keysPerThread);
 constexpr uint32_t kFusedRangeBeginXor = 0xFFFFFFFFu;  // begin = ranges[t].x ^ this
@@ -106,7 +128,7 @@ constexpr int kReportSeqShift = 40;
 constexpr unsigned long long kReportCountMask = (1ull << kReportSeqShift) - 1;
 cudaError_t launch_composite(const uint2* ranges, const uint32_t* ids, int idStrideWords, const ProjRecord* rec, void* framebuffer, int fbFormat,
                              int width, int height, int tilesX, int tilesY, float earlyOutT, int cullMode, uint32_t rangeBeginXor,
-                             const FrameReport& report, cudaStream_t stream);
+                             const FrameReport& report, cudaStream_t stream, bool pdl = false);
 
 // float target -> packed RGBA8 (R in the low byte), same pixel order as the target
 cudaError_t launch_present_rgba8(const void* framebuffer, int fbFormat, uint32_t* out, size_t pixels, cudaStream_t stream);

@@ -460,11 +460,14 @@ k_emit_sorted(const uint32_t* __restrict__ sortedVals, const uint2* __restrict__
     __shared__ uint32_t sBlockId;
     __shared__ uint32_t sWarpTotal[kEmitRounds][kWarps];
     __shared__ unsigned long long sBlockBase;
-    __shared__ uint32_t sDigit0[kRadixSize];  // histogram of the first tile digit (low byte of the tile id), one count per instance
+    __shared__ uint32_t sDigit0[2][kRadixSize];  // histograms of both tile digits (bits 0-7 and 8-15 of the tile id), one count per instance
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid == 0) sBlockId = atomicAdd(&ctr->projectTicket, 1u);  // dynamic id: predecessors are resident or done
-    sDigit0[tid] = 0;
+    sDigit0[0][tid] = 0;
+    sDigit0[1][tid] = 0;
+    pdl_wait();     // the depth-sorted list is the last depth pass's output
+    pdl_trigger();  // the first tile pass may be scheduled as this grid retires
     __syncthreads();
     const uint32_t vbid = sBlockId;
 
@@ -595,7 +598,11 @@ k_emit_sorted(const uint32_t* __restrict__ sortedVals, const uint2* __restrict__
                 const uint32_t tile = (y0 + row) * tilesX + (x0 + col);
                 keys[oOff + k] = tile;
                 vals[oOff + k] = oId;
-                if (tileDigitHist) smem_red_add(&sDigit0[tile & (kRadixSize - 1)], 1u);
+                if (tileDigitHist)
+                {
+                    smem_red_add(&sDigit0[0][tile & (kRadixSize - 1)], 1u);
+                    smem_red_add(&sDigit0[1][(tile >> kRadixBits) & (kRadixSize - 1)], 1u);
+                }
             }
         }
     }
@@ -613,8 +620,9 @@ k_emit_sorted(const uint32_t* __restrict__ sortedVals, const uint2* __restrict__
     }
     if (tileDigitHist)
     {
-        const uint32_t c = sDigit0[tid];
-        if (c) atomicAdd(tileDigitHist + tid, c);
+        const uint32_t c0 = sDigit0[0][tid], c1 = sDigit0[1][tid];
+        if (c0) atomicAdd(tileDigitHist + tid, c0);
+        if (c1) atomicAdd(tileDigitHist + kRadixSize + tid, c1);
     }
 }
 
@@ -636,6 +644,8 @@ k_project_keys(const PackedCloud cloud, const __grid_constant__ FrameConstants f
     // histogram pass nor accumulate the next digit's histogram while they scatter
     __shared__ uint32_t sDigit[kDepthBits / kRadixBits][kRadixSize];
     const int tid = threadIdx.x;
+    pdl_trigger();  // first kernel of the frame's chain (launched normally, after the control-block memset): the first depth
+                    // pass may be scheduled as this grid's CTAs retire; it waits for this grid before it reads anything
 #pragma unroll
     for (int p = 0; p < kDepthBits / kRadixBits; p++) sDigit[p][tid] = 0;
     __syncthreads();
@@ -872,14 +882,13 @@ cudaError_t launch_project_keys(const PackedCloud& cloud, const FrameConstants& 
 
 cudaError_t launch_emit_sorted(const uint32_t* sortedVals, const uint2* side, uint32_t n,
                                const FrameConstants& fc, uint32_t* keys, uint32_t* vals, FrameCounters* ctr,
-                               unsigned long long* scanState, uint32_t capacity, uint32_t* tileDigitHist, cudaStream_t stream)
+                               unsigned long long* scanState, uint32_t capacity, uint32_t* tileDigitHist, cudaStream_t stream, bool pdl)
 {
     const uint32_t perCta = kProjThreads * kEmitRounds;
     const uint32_t blocks = (n + perCta - 1) / perCta;  // <= project_num_blocks(n): scanState is large enough
     if (blocks == 0) return cudaSuccess;
-    k_emit_sorted<<<blocks, kProjThreads, 0, stream>>>(sortedVals, side, n, (uint32_t)fc.tilesX, keys, vals, ctr, scanState, capacity,
-                                                       tileDigitHist);
-    return cudaGetLastError();
+    return launch_kernel(k_emit_sorted, dim3(blocks), dim3(kProjThreads), 0, stream, pdl, sortedVals, side, n, (uint32_t)fc.tilesX, keys, vals, ctr, scanState,
+                         capacity, tileDigitHist);
 }
 
 uint32_t project_num_blocks(uint32_t n) { return (n + kProjThreads - 1) / kProjThreads; }

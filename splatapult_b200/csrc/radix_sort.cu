@@ -175,7 +175,7 @@ k_sort_onesweep(const KeyT* __restrict__ keysIn, const uint32_t* __restrict__ va
                 uint32_t* __restrict__ valsOut, const uint32_t* __restrict__ nDevice, int shift, uint32_t mask, int nextShift, uint32_t nextMask,
                 const uint32_t* __restrict__ histogram, uint32_t* __restrict__ histogramNext, unsigned long long* __restrict__ status,
                 uint32_t* __restrict__ ticket, uint32_t gen, unsigned long long* tl, uint2* __restrict__ tileRanges, uint32_t numRangeTiles,
-                uint32_t statusTiles, int rangeShift, unsigned long long* __restrict__ groupAgg)
+                uint32_t statusTiles, int rangeShift, unsigned long long* __restrict__ groupAgg, int histFromPredecessor)
 {
     using Smem = SortSmem<KPT, KeyT>;
     constexpr int kTile = Smem::kTile;
@@ -184,11 +184,16 @@ k_sort_onesweep(const KeyT* __restrict__ keysIn, const uint32_t* __restrict__ va
     Smem& s = *reinterpret_cast<Smem*>(smemRaw);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const uint32_t n = *nDevice;
-    const uint32_t numTiles = (n + kTile - 1) / kTile;
     const bool wantNext = histogramNext != nullptr;
     uint32_t* const statusLo = reinterpret_cast<uint32_t*>(status);
     uint32_t* const statusHi = statusLo + (size_t)statusTiles * kRadixSize;
+
+    // Programmatic dependent launch: this grid may be running while the pass before it drains.  The element count and a
+    // histogram row left by the frame's FIRST kernels (all digits known up front) predate that pass and may be read now;
+    // a row the preceding kernel itself produces, and the keys, only after pdl_wait().
+    if (histFromPredecessor) pdl_wait();
+    const uint32_t n = *nDevice;
+    const uint32_t numTiles = (n + kTile - 1) / kTile;
 
     // global exclusive scan of this pass's digit histogram: thread d owns digit d
     uint32_t digitStart;
@@ -231,6 +236,8 @@ k_sort_onesweep(const KeyT* __restrict__ keysIn, const uint32_t* __restrict__ va
         concentrated = sqAll * (float)kMatchAnyMaxValues > (float)n * (float)n;  // effective values < kMatchAnyMaxValues
         __syncthreads();
     }
+    if (!histFromPredecessor) pdl_wait();  // the keys are the preceding pass's output
+    pdl_trigger();                          // after the wait: see device_common.cuh
 
     uint32_t parity = 0;
     for (;;)
@@ -578,12 +585,17 @@ static cudaError_t launch_passes_t(KeyT* keysA, uint32_t* valsA, KeyT* keysB, ui
         const bool last = p == passes - 1;
         const bool wantNext = !last && !ws.allHistogramsReady;
         const int nshift = last ? 0 : shift + kRadixBits;
-        k_sort_onesweep<KPT, KeyT><<<grid, kSortThreads, sizeof(Smem), stream>>>(
+        // a histogram row written by the kernel right before this pass: the producer's for pass 0, the previous pass's when the
+        // passes accumulate each other's histograms
+        const int histFromPredecessor = (p == 0 || !ws.allHistogramsReady) ? 1 : 0;
+        cudaError_t le = launch_kernel(
+            k_sort_onesweep<KPT, KeyT>, dim3(grid), dim3(kSortThreads), sizeof(Smem), stream, ws.pdl,
             kin, vin, kout, vout, nDevice, shift, digit_mask(shift, endBit), nshift, last ? 0u : digit_mask(nshift, endBit),
-            ws.histograms + (ws.passOffset + p) * kRadixSize, wantNext ? ws.histograms + (ws.passOffset + p + 1) * kRadixSize : nullptr,
-            ws.status + (size_t)(ws.passOffset + p) * maxTiles * kRadixSize, ws.tickets + ws.passOffset + p, ws.generation, dTl ? dTl + p * tlWords : nullptr,
-            last && shift >= kRangeShift ? ws.tileRanges : nullptr, ws.numRangeTiles,  // the digit must be part of the tile id
-            (uint32_t)maxTiles, kRangeShift, ws.groupAgg ? ws.groupAgg + (size_t)p * ws.groupWordsPerPass : nullptr);
+            (const uint32_t*)(ws.histograms + (ws.passOffset + p) * kRadixSize), wantNext ? ws.histograms + (ws.passOffset + p + 1) * kRadixSize : (uint32_t*)nullptr,
+            ws.status + (size_t)(ws.passOffset + p) * maxTiles * kRadixSize, ws.tickets + ws.passOffset + p, ws.generation, dTl ? dTl + p * tlWords : (unsigned long long*)nullptr,
+            last && shift >= kRangeShift ? ws.tileRanges : (uint2*)nullptr, ws.numRangeTiles,  // the digit must be part of the tile id
+            (uint32_t)maxTiles, kRangeShift, ws.groupAgg ? ws.groupAgg + (size_t)p * ws.groupWordsPerPass : (unsigned long long*)nullptr, histFromPredecessor);
+        if (le != cudaSuccess) return le;
     }
 #ifdef SPL_SORT_TIMELINE
     if (tlPath)

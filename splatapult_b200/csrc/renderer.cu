@@ -56,6 +56,8 @@ struct RendererImpl
     bool profile = false;
     double instancesPerGaussian = 16.0;
     int sortMode = SPL_SORT_LSD;
+    bool pdlOption = true;  // SPL_OPT_PDL: chain the frame's kernels as programmatic dependent launches
+    bool usePdl() const { return pdlOption && !profile; }  // (stage events between the kernels would break the chain)
 
     // cloud
     bool initialized = false;
@@ -81,7 +83,17 @@ struct RendererImpl
     const unsigned long long* dSortedKeys = nullptr;  // where the last LSD sort left its result ...
     int sortedKeyBytes = 8;                           // ... as u64 (tile << 32 | depthKey) or, default path, u32 tile ids
     const uint32_t* dSortedVals = nullptr;
-    int sortKpt = 16;
+    int sortKptOption = 0;  // SPL_OPT_SORT_TILE: 0 = automatic (below), 8 = 2048-key tiles, 16 = 4096-key tiles
+    // keys per thread of a sort over at most `keys` elements.  The passes are latency bound per tile; when 4096-key tiles do
+    // not fill one wave of CTAs (1 M gaussians = 245 tiles on 592 slots) 2048-key tiles finish a pass sooner (measured:
+    // depth passes 104.6 -> 97.4 us at 1 M), with more tiles than slots the larger tile wins (6 M: 312 vs 337 us)
+    int kptFor(uint64_t keys) const
+    {
+        if (sortKptOption) return sortKptOption;
+        return (keys + kSortTileKeys - 1) / kSortTileKeys < (uint64_t)numSMs * 4 ? 8 : 16;
+    }
+    int depthKpt() const { return kptFor(n); }
+    int instKpt() const { return sortKptOption ? sortKptOption : 16; }  // the instance count is only known on the device
     uint2* dRanges = nullptr;
     uint32_t* dTileCtl = nullptr;  // tileCount | tileCursor | largeList, rangesTiles words each
     uint4* dSide = nullptr;        // per-gaussian {rect, depthKey, count} of the binned sort
@@ -282,8 +294,8 @@ struct RendererImpl
     // bytes of the control block a frame with `depthPasses` passes over the gaussians and `instPasses` over the instances clears
     size_t frameControlBytes(int depthPasses, int instPasses) const
     {
-        return controlBytes + ((size_t)depthPasses * sort_group_words(std::max<uint32_t>(n, 1), sortKpt) +
-                               (size_t)instPasses * sort_group_words(std::max<uint64_t>(capacity, 1), sortKpt)) * sizeof(unsigned long long);
+        return controlBytes + ((size_t)depthPasses * sort_group_words(std::max<uint32_t>(n, 1), depthKpt()) +
+                               (size_t)instPasses * sort_group_words(std::max<uint64_t>(capacity, 1), instKpt())) * sizeof(unsigned long long);
     }
 
     int initFromDevice(const void* dAos, size_t count, size_t stride, bool fullSH, bool srgbIn)
@@ -401,7 +413,7 @@ struct RendererImpl
         uint32_t* keysA32 = reinterpret_cast<uint32_t*>(dKeysA);
         uint32_t* keysB32 = reinterpret_cast<uint32_t*>(dKeysB);
         CU_TRY(launch_emit_sorted(order, reinterpret_cast<const uint2*>(dSide), n, fc, keysB32, dValsB, dCtr, dScan, (uint32_t)capacity,
-                                  dHist + 4 * kRadixSize, stream));
+                                  dHist + 4 * kRadixSize, stream, usePdl()));
         launches += n ? 1 : 0;
         if (profile) CU_TRY(cudaEventRecord(ev[6], stream));
         dSortedKeys = dKeysB;
@@ -409,9 +421,11 @@ struct RendererImpl
         sortedKeyBytes = 4;
         if (tilePasses > 0)
         {
-            SortWorkspace wsTile{dHist, dStatus, dCtr->sortTickets, capacity, sortGeneration, sortKpt, 4, rangesFused ? dRanges : nullptr, numTiles};
-            wsTile.groupAgg = dGroups + 4 * sort_group_words(std::max<uint32_t>(n, 1), sortKpt);
-            wsTile.groupWordsPerPass = sort_group_words(std::max<uint64_t>(capacity, 1), sortKpt);
+            SortWorkspace wsTile{dHist, dStatus, dCtr->sortTickets, capacity, sortGeneration, instKpt(), 4, rangesFused ? dRanges : nullptr, numTiles};
+            wsTile.allHistogramsReady = tilePasses <= 2;  // k_emit_sorted left the histograms of both tile digits
+            wsTile.pdl = usePdl();
+            wsTile.groupAgg = dGroups + 4 * sort_group_words(std::max<uint32_t>(n, 1), depthKpt());
+            wsTile.groupWordsPerPass = sort_group_words(std::max<uint64_t>(capacity, 1), instKpt());
             CU_TRY(launch_sort_passes32(keysB32, dValsB, keysA32, dValsA, &dCtr->usedInstances, capacity, 0, tileBits, wsTile, numSMs, stream));
             launches += tilePasses;
             if (tilePasses & 1) { dSortedKeys = dKeysA; dSortedVals = dValsA; }
@@ -494,7 +508,7 @@ struct RendererImpl
         {
             const int tilePassesNow = (sortBits - kDepthBits + kRadixBits - 1) / kRadixBits;
             const size_t clearBytes = frameSortMode == SPL_SORT_BINNED ? controlBytes
-                                      : frameSortMode == SPL_SORT_LSD_FLAT ? frameControlBytes(0, sortPasses) : frameControlBytes(4, tilePassesNow);
+                                      : frameSortMode == SPL_SORT_LSD_FLAT ? frameControlBytes(4, sortPasses) : frameControlBytes(4, tilePassesNow);
             CU_TRY(cudaMemsetAsync(dControl, 0, clearBytes, stream));
         }
         if (frameSortMode == SPL_SORT_BINNED)
@@ -541,9 +555,9 @@ struct RendererImpl
                 launches += n ? 1 : 0;
                 if (profile) CU_TRY(cudaEventRecord(ev[1], stream));
                 if (profile) CU_TRY(cudaEventRecord(ev[6], stream));
-                SortWorkspace ws{dHist, dStatus, dCtr->sortTickets, capacity, sortGeneration, sortKpt, 0, rangesFused ? dRanges : nullptr, numTiles};
-                ws.groupAgg = dGroups;
-                ws.groupWordsPerPass = sort_group_words(std::max<uint64_t>(capacity, 1), sortKpt);
+                SortWorkspace ws{dHist, dStatus, dCtr->sortTickets, capacity, sortGeneration, instKpt(), 0, rangesFused ? dRanges : nullptr, numTiles};
+                ws.groupAgg = dGroups + 4 * sort_group_words(std::max<uint32_t>(n, 1), depthKpt());  // same layout as the split path
+                ws.groupWordsPerPass = sort_group_words(std::max<uint64_t>(capacity, 1), instKpt());
                 CU_TRY(launch_sort_passes(dKeysA, dValsA, dKeysB, dValsB, &dCtr->usedInstances, capacity, 0, sortBits, ws, numSMs, stream));
                 launches += sortPasses;
                 sortedKeyBytes = 8;
@@ -566,10 +580,11 @@ struct RendererImpl
                 launches += n ? 1 : 0;
                 if (profile) CU_TRY(cudaEventRecord(ev[1], stream));
                 NvtxScope sortZone("sort");
-                SortWorkspace wsDepth{dHist, dStatus, dCtr->sortTickets, capacity, sortGeneration, sortKpt, 0};
+                SortWorkspace wsDepth{dHist, dStatus, dCtr->sortTickets, capacity, sortGeneration, depthKpt(), 0};
                 wsDepth.allHistogramsReady = true;  // k_project_keys left all four depth-digit histograms
+                wsDepth.pdl = usePdl();
                 wsDepth.groupAgg = dGroups;
-                wsDepth.groupWordsPerPass = sort_group_words(std::max<uint32_t>(n, 1), sortKpt);
+                wsDepth.groupWordsPerPass = sort_group_words(std::max<uint32_t>(n, 1), depthKpt());
                 CU_TRY(launch_sort_passes32(keysA32, dValsA, keysB32, dValsB, &dCtr->sortCount, capacity, 0, kDepthBits, wsDepth, numSMs, stream));
                 launches += 4;
                 // 4 passes: the sorted ids are back in dValsA
@@ -692,7 +707,8 @@ struct RendererImpl
         const FrameReport report{dCtr, dReport + seq % kReportRing, (seq & ((1ull << (64 - kReportSeqShift)) - 1)) << kReportSeqShift};
         nvtxRangePushA("draw");  // the reference's zone name (src/splatrenderer.cpp:323)
         const cudaError_t ce = launch_composite(dRanges, binned ? reinterpret_cast<const uint32_t*>(dKeysA) : sortedVals(), binned ? 2 : 1, dRec, dFb, fbFormat, fc.width,
-                                                fc.height, fc.tilesX, fc.tilesY, (float)earlyOutT, subblockCull, rangesFused ? kFusedRangeBeginXor : 0u, report, stream);
+                                                fc.height, fc.tilesX, fc.tilesY, (float)earlyOutT, subblockCull, rangesFused ? kFusedRangeBeginXor : 0u, report, stream,
+                                                usePdl() && frameSortMode == SPL_SORT_LSD);
         nvtxRangePop();
         CU_TRY(ce);
         frameSeq = seq;
@@ -1033,8 +1049,8 @@ bool SplatRenderer::SetOption(int option, double value)
     case SPL_OPT_PROFILE: impl->profile = value != 0.0; break;
     case SPL_OPT_INSTANCES_PER_GAUSSIAN: impl->instancesPerGaussian = value; break;
     case SPL_OPT_SORT_TILE:
-        if (value != 2048 && value != 4096) { status = SPL_ERR_ARG; error = "sort tile must be 2048 or 4096 keys"; return false; }
-        impl->sortKpt = value == 2048 ? 8 : 16;
+        if (value != 0 && value != 2048 && value != 4096) { status = SPL_ERR_ARG; error = "sort tile must be 0 (automatic), 2048 or 4096 keys"; return false; }
+        impl->sortKptOption = value == 0 ? 0 : (value == 2048 ? 8 : 16);
         break;
     case SPL_OPT_SORT_MODE:
         if (value != SPL_SORT_BINNED && value != SPL_SORT_LSD && value != SPL_SORT_LSD_FLAT) { status = SPL_ERR_ARG; error = "unknown sort mode"; return false; }
@@ -1045,6 +1061,10 @@ bool SplatRenderer::SetOption(int option, double value)
         if (value != 0 && value != 1) { status = SPL_ERR_ARG; error = "shared sort must be 0 or 1"; return false; }
         impl->sharedSort = value != 0;
         impl->haveSort = false;
+        break;
+    case SPL_OPT_PDL:
+        if (value != 0 && value != 1) { status = SPL_ERR_ARG; error = "pdl must be 0 or 1"; return false; }
+        impl->pdlOption = value != 0;
         break;
     case SPL_OPT_SUBBLOCK_CULL:
         if (value != 0 && value != 1 && value != 2) { status = SPL_ERR_ARG; error = "sub-block cull mode must be 0, 1 or 2"; return false; }
