@@ -781,7 +781,7 @@ def main():
     ap.add_argument("--sort-mode", default="lsd", choices=["binned", "lsd", "lsd_flat"])
     ap.add_argument("--sort-tile", type=int, default=0, choices=[0, 2048, 4096], help="onesweep tile: 0 = the library's automatic choice")
     ap.add_argument("--subblock-cull", type=int, default=2, choices=[0, 1, 2], help="compositor sub-block mask: 0 none, 1 box, 2 exact ellipse")
-    ap.add_argument("--pdl", type=int, default=1, choices=[0, 1], help="programmatic dependent launch of the frame's kernels (1 = default)")
+    ap.add_argument("--pdl", type=int, default=0, choices=[0, 1], help="programmatic dependent launch of the frame's kernels (1 = default)")
     ap.add_argument("--cpu-arm-child", action="store_true", help=argparse.SUPPRESS)
     ap.add_argument("--cpu-budget", type=float, default=150.0, help=argparse.SUPPRESS)
     ap.add_argument("--workload-json", default=None, help=argparse.SUPPRESS)

@@ -114,7 +114,7 @@ struct CompSmem
 
 template <bool HALF>
 __global__ void __launch_bounds__(kCompThreads, 6)
-k_composite(const uint2* __restrict__ ranges, const uint32_t* __restrict__ vals, int idStride, const ProjRecord* __restrict__ rec,
+k_composite(const uint2* ranges, const uint32_t* vals, int idStride, const ProjRecord* rec,
             void* __restrict__ fb, int width, int height, int tilesX, float earlyOutT, int cullMode, uint32_t beginXor, FrameReport report)
 {
     __shared__ CompSmem s;
@@ -162,11 +162,12 @@ k_composite(const uint2* __restrict__ ranges, const uint32_t* __restrict__ vals,
         have = (uint32_t)tid < cnt;
         if (have)
         {
-            const uint32_t id = __ldg(vals + (size_t)(hi - 1 - tid) * idStride);  // nearest first
+            // plain loads (not __ldg / the read-only path): ptxas may move LDG.CONSTANT loads above pdl_wait()
+            const uint32_t id = vals[(size_t)(hi - 1 - tid) * idStride];  // nearest first
             const float4* p = reinterpret_cast<const float4*>(rec + id);
-            q0 = __ldg(p);      // px, py, i00, i01
-            q1 = __ldg(p + 1);  // i10, i11, r, g
-            q2 = __ldg(p + 2);  // b, alpha, key, visible
+            q0 = p[0];  // px, py, i00, i01
+            q1 = p[1];  // i10, i11, r, g
+            q2 = p[2];  // b, alpha, key, visible
         }
     };
     auto stage = [&](int buf) {

@@ -194,6 +194,10 @@ __device__ __forceinline__ float sqrt_approx(float x)
 //                    of this one has triggered (or exited), so the next kernel's code BEFORE its wait runs after this
 //                    kernel's predecessor has completed, but concurrently with this kernel's tail.
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+// NOTE: data the preceding kernels produce must not be read through the read-only path (`const T* __restrict__` parameters,
+// __ldg): those loads are LDG.CONSTANT, which the compiler and ptxas move freely -- also above this wait (seen in the SASS:
+// the sorter's histogram read sat above ACQBULK and read the row before its producer had finished).  Use plain or
+// ld.relaxed loads for such data.
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
 __device__ __forceinline__ uint32_t lanemask_lt()

@@ -172,8 +172,8 @@ struct SortSmem
 template <int KPT, typename KeyT>
 __global__ void __launch_bounds__(kSortThreads, KPT == 16 ? (sizeof(KeyT) == 4 ? 4 : 3) : 5)
 k_sort_onesweep(const KeyT* __restrict__ keysIn, const uint32_t* __restrict__ valsIn, KeyT* __restrict__ keysOut,
-                uint32_t* __restrict__ valsOut, const uint32_t* __restrict__ nDevice, int shift, uint32_t mask, int nextShift, uint32_t nextMask,
-                const uint32_t* __restrict__ histogram, uint32_t* __restrict__ histogramNext, unsigned long long* __restrict__ status,
+                uint32_t* __restrict__ valsOut, const uint32_t* nDevice, int shift, uint32_t mask, int nextShift, uint32_t nextMask,
+                const uint32_t* histogram, uint32_t* __restrict__ histogramNext, unsigned long long* __restrict__ status,
                 uint32_t* __restrict__ ticket, uint32_t gen, unsigned long long* tl, uint2* __restrict__ tileRanges, uint32_t numRangeTiles,
                 uint32_t statusTiles, int rangeShift, unsigned long long* __restrict__ groupAgg, int histFromPredecessor)
 {
@@ -192,7 +192,8 @@ k_sort_onesweep(const KeyT* __restrict__ keysIn, const uint32_t* __restrict__ va
     // histogram row left by the frame's FIRST kernels (all digits known up front) predate that pass and may be read now;
     // a row the preceding kernel itself produces, and the keys, only after pdl_wait().
     if (histFromPredecessor) pdl_wait();
-    const uint32_t n = *nDevice;
+    // (strong loads, not the read-only path: ptxas moves LDG.CONSTANT loads above the wait)
+    const uint32_t n = ld_relaxed_u32(nDevice);
     const uint32_t numTiles = (n + kTile - 1) / kTile;
 
     // global exclusive scan of this pass's digit histogram: thread d owns digit d
@@ -200,7 +201,7 @@ k_sort_onesweep(const KeyT* __restrict__ keysIn, const uint32_t* __restrict__ va
     bool concentrated;
     bool digitUsed;  // no key of this pass has digit `tid`: nobody needs its offsets, so it takes no part in the look-back
     {
-        const uint32_t h = histogram[tid];
+        const uint32_t h = ld_relaxed_u32(histogram + tid);
         digitUsed = h != 0;
         uint32_t incl = h;
 #pragma unroll

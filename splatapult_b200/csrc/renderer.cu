@@ -56,7 +56,7 @@ struct RendererImpl
     bool profile = false;
     double instancesPerGaussian = 16.0;
     int sortMode = SPL_SORT_LSD;
-    bool pdlOption = true;  // SPL_OPT_PDL: chain the frame's kernels as programmatic dependent launches
+    bool pdlOption = false;  // SPL_OPT_PDL: chain the frame's kernels as programmatic dependent launches
     bool usePdl() const { return pdlOption && !profile; }  // (stage events between the kernels would break the chain)
 
     // cloud
