@@ -155,6 +155,9 @@ enum {
     SPL_OPT_SORT_MODE = 3,    /* SPL_SORT_LSD (default), SPL_SORT_LSD_FLAT or SPL_SORT_BINNED; all give bit-identical tile lists */
     SPL_OPT_SUBBLOCK_CULL = 5, /* compositor's per-entry 8x4 sub-block mask: 0 none, 1 footprint box, 2 exact ellipse (default);
                                  culling only skips lanes whose weight is discarded anyway: images are bit-identical */
+    SPL_OPT_GRAPH = 8,        /* 1: the device work of a Sort (control-block memset + projection + all sort passes) is captured and
+                                 replayed as ONE CUDA graph; the executable graph is updated in place every frame (the camera
+                                 changes the kernel arguments).  0 (default): individual launches.  Results are identical. */
     SPL_OPT_PDL = 7,          /* 1 (default): the kernels of a frame are chained as programmatic dependent launches (a kernel's
                                  prologue overlaps the tail of the one before it; griddepcontrol.wait guards every dependent
                                  read).  0: plain stream order.  Results are identical. */

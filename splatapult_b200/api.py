@@ -20,6 +20,7 @@ OPT_SORT_TILE = 4
 OPT_SUBBLOCK_CULL = 5
 OPT_SHARED_SORT = 6
 OPT_PDL = 7
+OPT_GRAPH = 8
 SORT_BINNED = 0
 SORT_LSD = 1
 SORT_LSD_FLAT = 2

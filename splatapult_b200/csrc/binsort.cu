@@ -15,6 +15,8 @@
 //      Segments too long for shared memory (> 12288 instances in one 16x16 tile) ping-pong through global memory.
 // The stand-alone LSD onesweep sorter (radix_sort.cu) remains selectable (SPL_OPT_SORT_MODE) and is what
 // spl_sorter_* exposes.
+#include <mutex>
+
 #include "device_common.cuh"
 #include "kernels.h"
 
@@ -255,9 +257,11 @@ cudaError_t launch_tile_scan(const uint32_t* tileCount, uint32_t numTiles, uint2
 cudaError_t launch_segment_sort(unsigned long long* pairs, unsigned long long* scratch, const uint2* ranges, uint32_t numTiles,
                                 const uint32_t* largeList, const FrameCounters* ctr, int numSMs, cudaStream_t stream)
 {
+    static std::mutex attrMutex;  // cudaFuncSetAttribute is per device: one table, filled under a lock
     static bool attrSet[64] = {};
     int dev = 0;
     cudaGetDevice(&dev);
+    std::lock_guard<std::mutex> lock(attrMutex);
     if (!attrSet[dev & 63])
     {
         cudaError_t e = cudaFuncSetAttribute(k_segment_sort_large, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSegLargeSmemBytes);

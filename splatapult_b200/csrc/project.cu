@@ -22,6 +22,7 @@
 // Frame counters (visible, usedInstances, ...) take ONE atomic per CTA: a per-warp atomicAdd on one L2 address was,
 // at N/32 serialised operations, the whole run time of the projection kernel until it was found.
 #include <cstdlib>
+#include <mutex>
 
 #include "device_common.cuh"
 #include "kernels.h"
@@ -901,17 +902,27 @@ cudaError_t launch_project_keys(const PackedCloud& cloud, const FrameConstants& 
     if (blocks == 0) return cudaSuccess;
     // persistent, grid-stride: as many CTAs as are resident at once (a multiple of the SM count), times `waves`
     // (SPL_PROJECT_WAVES overrides, for tuning)
-    static int ctasPerWave[4] = {0, 0, 0, 0};
+    // per device (the SM count and the occupancy are the device's), filled once under a lock: renderers on several GPUs or
+    // threads of one process share this table
+    static std::mutex cacheMutex;
+    static int ctasPerWaveCache[64][4] = {};
     const int mode = cloud.shMode == 0 ? 0 : (cloud.shMode == 1 ? 1 : 3);
-    if (!ctasPerWave[mode])
+    int dev = 0;
+    cudaGetDevice(&dev);
+    int ctasPerWave[4] = {0, 0, 0, 0};
     {
-        int dev = 0, numSMs = 0, occ = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&numSMs, cudaDevAttrMultiProcessorCount, dev);
-        if (mode == 0) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_project_keys<0>, kProjThreads, 0);
-        else if (mode == 1) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_project_keys<1>, kProjThreads, 0);
-        else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_project_keys<3>, kProjThreads, 0);
-        ctasPerWave[mode] = (numSMs > 0 ? numSMs : 148) * (occ > 0 ? occ : 4);
+        std::lock_guard<std::mutex> lock(cacheMutex);
+        int& slot = ctasPerWaveCache[dev & 63][mode];
+        if (!slot)
+        {
+            int numSMs = 0, occ = 0;
+            cudaDeviceGetAttribute(&numSMs, cudaDevAttrMultiProcessorCount, dev);
+            if (mode == 0) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_project_keys<0>, kProjThreads, 0);
+            else if (mode == 1) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_project_keys<1>, kProjThreads, 0);
+            else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_project_keys<3>, kProjThreads, 0);
+            slot = (numSMs > 0 ? numSMs : 148) * (occ > 0 ? occ : 4);
+        }
+        ctasPerWave[mode] = slot;
     }
     // measured: one wave is best for the light kernels (34 us vs 40 / 43 us with 2 / 4 waves at 1 M gaussians, deg 0); the
     // degree-3 kernel (89 registers, 2 CTAs per SM) balances its tail better with 4 (302 vs 311 us at 6 M)

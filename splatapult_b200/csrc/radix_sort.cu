@@ -21,6 +21,7 @@
 //   * the last pass of a frame sort also writes every tile's [begin, end) range (SortWorkspace::tileRanges).
 #include <cstdio>
 #include <cstdlib>
+#include <mutex>
 #include <vector>
 #include "device_common.cuh"
 #include "kernels.h"
@@ -552,14 +553,19 @@ static cudaError_t launch_passes_t(KeyT* keysA, uint32_t* valsA, KeyT* keysB, ui
 {
     using Smem = SortSmem<KPT, KeyT>;
     constexpr int kRangeShift = sizeof(KeyT) == 8 ? 32 : 0;  // where the tile id sits in a key
-    static bool attrSet[64] = {};
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (!attrSet[dev & 63])
     {
-        cudaError_t e = cudaFuncSetAttribute(k_sort_onesweep<KPT, KeyT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem));
-        if (e != cudaSuccess) return e;
-        attrSet[dev & 63] = true;
+        // cudaFuncSetAttribute is per device; one table per kernel instantiation, filled under a lock
+        static std::mutex attrMutex;
+        static bool attrSet[64] = {};
+        int dev = 0;
+        cudaGetDevice(&dev);
+        std::lock_guard<std::mutex> lock(attrMutex);
+        if (!attrSet[dev & 63])
+        {
+            cudaError_t e = cudaFuncSetAttribute(k_sort_onesweep<KPT, KeyT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem));
+            if (e != cudaSuccess) return e;
+            attrSet[dev & 63] = true;
+        }
     }
     const int passes = (endBit - beginBit + kRadixBits - 1) / kRadixBits;
     const uint64_t maxTiles = (capacity + kSortMinTileKeys - 1) / kSortMinTileKeys + 1;
@@ -618,15 +624,19 @@ static cudaError_t launch_passes_t(KeyT* keysA, uint32_t* valsA, KeyT* keysB, ui
 cudaError_t launch_sort_histogram(const unsigned long long* keysA, const uint32_t* nDevice, uint64_t capacity, int beginBit, int endBit,
                                   const SortWorkspace& ws, int numSMs, cudaStream_t stream)
 {
-    static bool attrSet[64] = {};
-    int dev = 0;
-    cudaGetDevice(&dev);
     const size_t smem = 2 * kSortTileKeys * sizeof(unsigned long long);
-    if (!attrSet[dev & 63])
     {
-        cudaError_t e = cudaFuncSetAttribute(k_sort_histogram, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        attrSet[dev & 63] = true;
+        static std::mutex attrMutex;
+        static bool attrSet[64] = {};
+        int dev = 0;
+        cudaGetDevice(&dev);
+        std::lock_guard<std::mutex> lock(attrMutex);
+        if (!attrSet[dev & 63])
+        {
+            cudaError_t e = cudaFuncSetAttribute(k_sort_histogram, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return e;
+            attrSet[dev & 63] = true;
+        }
     }
     const uint32_t capTiles = (uint32_t)((capacity + kSortTileKeys - 1) / kSortTileKeys);
     const uint32_t grid = max(1u, min((uint32_t)numSMs * 3u, capTiles));

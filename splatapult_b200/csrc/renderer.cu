@@ -56,6 +56,9 @@ struct RendererImpl
     bool profile = false;
     double instancesPerGaussian = 16.0;
     int sortMode = SPL_SORT_LSD;
+    bool graphOption = false;          // SPL_OPT_GRAPH: replay a Sort's device work as one CUDA graph
+    cudaGraphExec_t sortExec = nullptr;
+    uint64_t warmFrames = 0;           // frames enqueued directly since the last configuration change
     bool pdlOption = false;  // SPL_OPT_PDL: chain the frame's kernels as programmatic dependent launches
     bool usePdl() const { return pdlOption && !profile; }  // (stage events between the kernels would break the chain)
 
@@ -185,6 +188,8 @@ struct RendererImpl
         stream = nullptr;
         ownStream = false;
         initialized = false;
+        if (sortExec) cudaGraphExecDestroy(sortExec);
+        sortExec = nullptr;
         if (hReport) cudaFreeHost(hReport);
         hReport = dReport = nullptr;
     }
@@ -450,57 +455,9 @@ struct RendererImpl
         return incomplete ? fail(SPL_ERR_OVERFLOW, rep) : ok();
     }
 
-    int sortImpl(const float* cam, const float* proj, const float* vp, const float* nf)
+    // the device work of one Sort: control-block memset + projection + sort passes (+ tile ranges), enqueued on `stream`
+    int enqueueSortWork(uint32_t numTiles)
     {
-        if (int rc = begin()) return rc;
-        if (!initialized) return fail(SPL_ERR_ARG, "Sort before Init");
-        if (growTo > capacity)
-        {
-            if (int rc = reserve(growTo)) return rc;  // an earlier frame overflowed (pollReports)
-        }
-        growTo = 0;
-        if (vp[0] != 0.0f || vp[1] != 0.0f) return fail(SPL_ERR_ARG, "viewport origin must be (0,0) (the reference assumes it, SURVEY q6)");
-        const int W = (int)vp[2], H = (int)vp[3];
-        if (W <= 0 || H <= 0 || (float)W != vp[2] || (float)H != vp[3]) return fail(SPL_ERR_ARG, "viewport width/height must be positive integers");
-        const int tilesX = (W + kTileW - 1) / kTileW, tilesY = (H + kTileH - 1) / kTileH;
-        if (tilesX > 1024 || tilesY > 1024) return fail(SPL_ERR_ARG, "viewport larger than 32768 x 16384 pixels");
-
-        // frame constants, computed as the reference's CPU side does (float, glm operation order)
-        const mat4 camera = mat4::from(cam), projM = mat4::from(proj);
-        const mat4 view = inverse(camera);          // src/splatrenderer.cpp:161,327
-        const mat4 mvp = mul(projM, view);          // src/splatrenderer.cpp:175
-        std::memcpy(fc.view, view.m, 64);
-        std::memcpy(fc.mvp, mvp.m, 64);
-        std::memcpy(fc.proj, projM.m, 64);
-        fc.eye[0] = camera.at(3, 0); fc.eye[1] = camera.at(3, 1); fc.eye[2] = camera.at(3, 2);  // :328
-        fc.W = vp[2]; fc.H = vp[3]; fc.zNear = nf[0]; fc.zFar = nf[1];
-        fc.width = W; fc.height = H; fc.tilesX = tilesX; fc.tilesY = tilesY;
-        fc.srgb = srgb ? 1 : 0;
-        fc.zFarSort = nf[1];
-        fc.stereoPass = (sharedSort && sortMode == SPL_SORT_LSD) ? 1 : 0;
-        std::memcpy(lastArgs, cam, 64); std::memcpy(lastArgs + 16, proj, 64); std::memcpy(lastArgs + 32, vp, 16); std::memcpy(lastArgs + 36, nf, 8);
-        std::memcpy(drawArgs, lastArgs, sizeof drawArgs);
-
-        const uint32_t numTiles = (uint32_t)tilesX * tilesY;
-        if (numTiles > rangesTiles)
-        {
-            CU_TRY(cudaStreamSynchronize(stream));
-            cudaFree(dTileCtl);
-            dTileCtl = nullptr;
-            if (int rc = allocControl(numTiles)) return rc;
-            CU_TRY(cudaMalloc(&dTileCtl, (size_t)numTiles * 3 * sizeof(uint32_t)));
-            rangesTiles = numTiles;
-        }
-        int tileBits = 0;
-        while ((1u << tileBits) < numTiles) tileBits++;
-        sortBits = kDepthBits + tileBits;
-        sortPasses = (sortBits + kRadixBits - 1) / kRadixBits;
-
-        if (profile && !evCreated)
-        {
-            for (auto& e : ev) CU_TRY(cudaEventCreate(&e));
-            evCreated = true;
-        }
         launches = 0;
         frameSortMode = sortMode;
         rangesFused = false;
@@ -525,7 +482,7 @@ struct RendererImpl
             NvtxScope sortZone("sort");
             if (profile) CU_TRY(cudaEventRecord(ev[1], stream));
             CU_TRY(launch_tile_scan(tileCount, numTiles, dRanges, tileCursor, largeList, dCtr, (uint32_t)capacity, stream));
-            CU_TRY(launch_bin_instances(dSide, n, tilesX, tileCursor, dKeysA, (uint32_t)capacity, stream));
+            CU_TRY(launch_bin_instances(dSide, n, fc.tilesX, tileCursor, dKeysA, (uint32_t)capacity, stream));
             if (profile) CU_TRY(cudaEventRecord(ev[6], stream));
             CU_TRY(launch_segment_sort(dKeysA, dKeysB, dRanges, numTiles, largeList, dCtr, numSMs, stream));
             if (profile) CU_TRY(cudaEventRecord(ev[2], stream));
@@ -604,6 +561,96 @@ struct RendererImpl
             }
             if (profile) CU_TRY(cudaEventRecord(ev[3], stream));
         }
+        return 0;
+    }
+
+    int sortImpl(const float* cam, const float* proj, const float* vp, const float* nf)
+    {
+        if (int rc = begin()) return rc;
+        if (!initialized) return fail(SPL_ERR_ARG, "Sort before Init");
+        if (growTo > capacity)
+        {
+            if (int rc = reserve(growTo)) return rc;  // an earlier frame overflowed (pollReports)
+        }
+        growTo = 0;
+        if (vp[0] != 0.0f || vp[1] != 0.0f) return fail(SPL_ERR_ARG, "viewport origin must be (0,0) (the reference assumes it, SURVEY q6)");
+        const int W = (int)vp[2], H = (int)vp[3];
+        if (W <= 0 || H <= 0 || (float)W != vp[2] || (float)H != vp[3]) return fail(SPL_ERR_ARG, "viewport width/height must be positive integers");
+        const int tilesX = (W + kTileW - 1) / kTileW, tilesY = (H + kTileH - 1) / kTileH;
+        if (tilesX > 1024 || tilesY > 1024) return fail(SPL_ERR_ARG, "viewport larger than 32768 x 16384 pixels");
+
+        // frame constants, computed as the reference's CPU side does (float, glm operation order)
+        const mat4 camera = mat4::from(cam), projM = mat4::from(proj);
+        const mat4 view = inverse(camera);          // src/splatrenderer.cpp:161,327
+        const mat4 mvp = mul(projM, view);          // src/splatrenderer.cpp:175
+        std::memcpy(fc.view, view.m, 64);
+        std::memcpy(fc.mvp, mvp.m, 64);
+        std::memcpy(fc.proj, projM.m, 64);
+        fc.eye[0] = camera.at(3, 0); fc.eye[1] = camera.at(3, 1); fc.eye[2] = camera.at(3, 2);  // :328
+        fc.W = vp[2]; fc.H = vp[3]; fc.zNear = nf[0]; fc.zFar = nf[1];
+        fc.width = W; fc.height = H; fc.tilesX = tilesX; fc.tilesY = tilesY;
+        fc.srgb = srgb ? 1 : 0;
+        fc.zFarSort = nf[1];
+        fc.stereoPass = (sharedSort && sortMode == SPL_SORT_LSD) ? 1 : 0;
+        std::memcpy(lastArgs, cam, 64); std::memcpy(lastArgs + 16, proj, 64); std::memcpy(lastArgs + 32, vp, 16); std::memcpy(lastArgs + 36, nf, 8);
+        std::memcpy(drawArgs, lastArgs, sizeof drawArgs);
+
+        const uint32_t numTiles = (uint32_t)tilesX * tilesY;
+        if (numTiles > rangesTiles)
+        {
+            CU_TRY(cudaStreamSynchronize(stream));
+            cudaFree(dTileCtl);
+            dTileCtl = nullptr;
+            if (int rc = allocControl(numTiles)) return rc;
+            CU_TRY(cudaMalloc(&dTileCtl, (size_t)numTiles * 3 * sizeof(uint32_t)));
+            rangesTiles = numTiles;
+        }
+        int tileBits = 0;
+        while ((1u << tileBits) < numTiles) tileBits++;
+        sortBits = kDepthBits + tileBits;
+        sortPasses = (sortBits + kRadixBits - 1) / kRadixBits;
+
+        if (profile && !evCreated)
+        {
+            for (auto& e : ev) CU_TRY(cudaEventCreate(&e));
+            evCreated = true;
+        }
+        // SPL_OPT_GRAPH: the frame's memset + kernels are captured and replayed as one CUDA graph (parameters change every
+        // frame, so the capture is repeated and the executable graph UPDATED, not re-instantiated); the first frame after a
+        // configuration change runs directly (lazy one-time CUDA calls -- occupancy queries, function attributes -- must
+        // not land inside a capture)
+        const bool useGraph = graphOption && !profile && warmFrames >= 1;
+        if (useGraph)
+        {
+            CU_TRY(cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal));
+            const int rc = enqueueSortWork(numTiles);
+            cudaGraph_t g = nullptr;
+            const cudaError_t ce = cudaStreamEndCapture(stream, &g);  // always: the stream must leave capture mode
+            if (rc) { if (g) cudaGraphDestroy(g); return rc; }
+            if (ce != cudaSuccess) return fail(SPL_ERR_CUDA, std::string("cudaStreamEndCapture: ") + cudaGetErrorString(ce));
+            bool haveExec = false;
+            if (sortExec)
+            {
+                cudaGraphExecUpdateResultInfo info{};
+                haveExec = cudaGraphExecUpdate(sortExec, g, &info) == cudaSuccess;
+                if (!haveExec)
+                {
+                    cudaGetLastError();  // topology changed (other pass count / kernel variant): instantiate again
+                    cudaGraphExecDestroy(sortExec);
+                    sortExec = nullptr;
+                }
+            }
+            cudaError_t ie = cudaSuccess;
+            if (!haveExec) ie = cudaGraphInstantiate(&sortExec, g, 0);
+            cudaGraphDestroy(g);
+            if (ie != cudaSuccess) { sortExec = nullptr; return fail(SPL_ERR_CUDA, std::string("cudaGraphInstantiate: ") + cudaGetErrorString(ie)); }
+            CU_TRY(cudaGraphLaunch(sortExec, stream));
+        }
+        else
+        {
+            if (int rc = enqueueSortWork(numTiles)) return rc;
+        }
+        warmFrames++;
         haveSort = true;
         return ok();
     }
@@ -1061,6 +1108,11 @@ bool SplatRenderer::SetOption(int option, double value)
         if (value != 0 && value != 1) { status = SPL_ERR_ARG; error = "shared sort must be 0 or 1"; return false; }
         impl->sharedSort = value != 0;
         impl->haveSort = false;
+        break;
+    case SPL_OPT_GRAPH:
+        if (value != 0 && value != 1) { status = SPL_ERR_ARG; error = "graph must be 0 or 1"; return false; }
+        impl->graphOption = value != 0;
+        impl->warmFrames = 0;
         break;
     case SPL_OPT_PDL:
         if (value != 0 && value != 1) { status = SPL_ERR_ARG; error = "pdl must be 0 or 1"; return false; }
