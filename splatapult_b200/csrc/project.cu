@@ -452,7 +452,7 @@ k_project(const PackedCloud cloud, const __grid_constant__ FrameConstants fc, Pr
 // ---------------------------------------------------------------------------------------------------
 constexpr int kEmitRounds = 4;
 
-__global__ void __launch_bounds__(kProjThreads, 5)
+__global__ void __launch_bounds__(kProjThreads)
 k_emit_sorted(const uint32_t* sortedVals, const uint2* side,
               uint32_t nSorted, uint32_t tilesX, uint32_t* __restrict__ keys, uint32_t* __restrict__ vals,
               FrameCounters* __restrict__ ctr, unsigned long long* __restrict__ scanState, uint32_t capacity, uint32_t* __restrict__ tileDigitHist)
@@ -555,14 +555,10 @@ k_emit_sorted(const uint32_t* sortedVals, const uint2* side,
     }
     __syncthreads();
 
-    // ---- emission, one round at a time.  A lane generates the instances of ITS entry one after the other (tile ids advance
-    // along the rectangle's rows: no division, no search for an owner) while its count is small -- the common case: 2-3
-    // tiles per gaussian; the warp runs as many steps as its largest small entry has tiles.  The warp's instances form one
-    // contiguous run of the output: they are staged in shared memory at their position in that run and then copied out with
-    // coalesced stores.  Entries with more than kEmitSerialMax tiles (large or close splats, up to thousands of tiles) are
-    // rare: a warp that holds one writes its small entries directly and spreads each large one over its 32 lanes.
-    constexpr uint32_t kEmitSerialMax = 12;
-    __shared__ uint2 sStage[kWarps][kEmitSerialMax * 32];  // {tile id, gaussian id}
+    // ---- warp-cooperative, coalesced emission, one round at a time
+    // (measured alternatives, round 2: every lane writing its own entry's instances serially -- a third of the instructions,
+    // but scattered partial-sector stores: 103 vs 99 us for sort+emit at 1 M, 302 vs 316 at 6 M; the same with the warp's run
+    // staged in shared memory and copied out coalesced: 110 / 323 us.  The kernel's time is its scan chain, not the emission.)
     const unsigned long long blockBase = sBlockBase;
     uint32_t usedEnd = 0;
 #pragma unroll
@@ -575,77 +571,38 @@ k_emit_sorted(const uint32_t* sortedVals, const uint2* side,
         const uint32_t gOff = fits ? (uint32_t)gOff64 : 0u;
         if (cntE) usedEnd = max(usedEnd, gOff + cntE);
 
-        const uint32_t w = (rect[r] >> 20) + 1, x0 = rect[r] & 1023u, y0 = (rect[r] >> 10) & 1023u;
-        const bool big = cntE > kEmitSerialMax;
-        const uint32_t nSerial = big ? 0u : cntE;
-        const uint32_t steps = __reduce_max_sync(0xffffffffu, nSerial);
-        uint32_t rowTile = y0 * tilesX + x0, col = 0;
-        uint32_t bigMask = __ballot_sync(0xffffffffu, big);
-        if (bigMask == 0u)
+        uint32_t inclE = cntE;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1)
         {
-            // staged: position in the warp's run = exclusive prefix of the counts (entries that do not fit are a suffix)
-            const uint32_t pos = incl[r] - count[r];
-            for (uint32_t k = 0; k < steps; k++)
-            {
-                if (k < nSerial)
-                {
-                    sStage[warp][pos + k] = make_uint2(rowTile + col, id[r]);
-                    if (++col == w)
-                    {
-                        col = 0;
-                        rowTile += tilesX;
-                    }
-                }
-            }
-            const uint32_t total = __reduce_max_sync(0xffffffffu, cntE ? pos + cntE : 0u);
-            const uint32_t runBase = (uint32_t)(blockBase + base[r]);  // only used when total > 0, i.e. it fits 32 bits
-            __syncwarp();
-            for (uint32_t j = lane; j < total; j += 32)
-            {
-                const uint2 e = sStage[warp][j];
-                keys[runBase + j] = e.x;
-                vals[runBase + j] = e.y;
-                if (tileDigitHist)
-                {
-                    smem_red_add(&sDigit0[0][e.x & (kRadixSize - 1)], 1u);
-                    smem_red_add(&sDigit0[1][(e.x >> kRadixBits) & (kRadixSize - 1)], 1u);
-                }
-            }
-            __syncwarp();  // the stage is reused by the next round
-            continue;
+            const uint32_t v = __shfl_up_sync(0xffffffffu, inclE, d);
+            if (lane >= d) inclE += v;
         }
-        for (uint32_t k = 0; k < steps; k++)
+        const uint32_t wexE = inclE - cntE;
+        const uint32_t T = __shfl_sync(0xffffffffu, inclE, 31);
+        for (uint32_t j0 = 0; j0 < T; j0 += 32)
         {
-            if (k < nSerial)
+            const uint32_t j = j0 + lane;
+            int owner = 0;
+#pragma unroll
+            for (int s = 16; s; s >>= 1)
             {
-                const uint32_t tile = rowTile + col;
-                keys[gOff + k] = tile;
-                vals[gOff + k] = id[r];
-                if (tileDigitHist)
-                {
-                    smem_red_add(&sDigit0[0][tile & (kRadixSize - 1)], 1u);
-                    smem_red_add(&sDigit0[1][(tile >> kRadixBits) & (kRadixSize - 1)], 1u);
-                }
-                if (++col == w)
-                {
-                    col = 0;
-                    rowTile += tilesX;
-                }
+                const int cand = owner + s;
+                const uint32_t v = __shfl_sync(0xffffffffu, wexE, cand);
+                if (v <= j) owner = cand;
             }
-        }
-        while (bigMask)
-        {
-            const int src = __ffs(bigMask) - 1;
-            bigMask &= bigMask - 1u;
-            const uint32_t oCnt = __shfl_sync(0xffffffffu, cntE, src), oOff = __shfl_sync(0xffffffffu, gOff, src);
-            const uint32_t oW = __shfl_sync(0xffffffffu, w, src), oTile0 = __shfl_sync(0xffffffffu, y0 * tilesX + x0, src);
-            const uint32_t oId = __shfl_sync(0xffffffffu, id[r], src);
-            for (uint32_t j = lane; j < oCnt; j += 32)
+            const uint32_t oBase = __shfl_sync(0xffffffffu, wexE, owner);
+            const uint32_t oOff = __shfl_sync(0xffffffffu, gOff, owner);
+            const uint32_t oRect = __shfl_sync(0xffffffffu, rect[r], owner);
+            const uint32_t oId = __shfl_sync(0xffffffffu, id[r], owner);
+            if (j < T)
             {
-                const uint32_t row = j / oW, c = j - row * oW;
-                const uint32_t tile = oTile0 + row * tilesX + c;
-                keys[oOff + j] = tile;
-                vals[oOff + j] = oId;
+                const uint32_t k = j - oBase;
+                const uint32_t w = (oRect >> 20) + 1, x0 = oRect & 1023u, y0 = (oRect >> 10) & 1023u;
+                const uint32_t row = k / w, col = k - row * w;
+                const uint32_t tile = (y0 + row) * tilesX + (x0 + col);
+                keys[oOff + k] = tile;
+                vals[oOff + k] = oId;
                 if (tileDigitHist)
                 {
                     smem_red_add(&sDigit0[0][tile & (kRadixSize - 1)], 1u);

@@ -548,7 +548,6 @@ struct RendererImpl
                 if (fc.stereoPass == 1)
                 {
                     // the tile passes reuse dValsA: keep the depth order for the other eye's Render
-                    if (!dOrder) CU_TRY(cudaMalloc(&dOrder, std::max<size_t>(n, 1) * sizeof(uint32_t)));
                     CU_TRY(cudaMemcpyAsync(dOrder, dValsA, (size_t)n * sizeof(uint32_t), cudaMemcpyDeviceToDevice, stream));
                 }
                 if (int rc = expandAndSortTiles(dValsA, numTiles)) return rc;
@@ -619,6 +618,7 @@ struct RendererImpl
         // frame, so the capture is repeated and the executable graph UPDATED, not re-instantiated); the first frame after a
         // configuration change runs directly (lazy one-time CUDA calls -- occupancy queries, function attributes -- must
         // not land inside a capture)
+        if (fc.stereoPass == 1 && !dOrder) CU_TRY(cudaMalloc(&dOrder, std::max<size_t>(n, 1) * sizeof(uint32_t)));  // not inside a capture
         const bool useGraph = graphOption && !profile && warmFrames >= 1;
         if (useGraph)
         {
