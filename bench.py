@@ -347,8 +347,10 @@ class Rig:
         r.SetOption(api.OPT_SORT_MODE, {"lsd": api.SORT_LSD, "lsd_flat": api.SORT_LSD_FLAT, "binned": api.SORT_BINNED}[a.sort_mode])
         r.SetOption(api.OPT_SORT_TILE, a.sort_tile)
         r.SetOption(api.OPT_SUBBLOCK_CULL, a.subblock_cull)
-        r.SetOption(api.OPT_PDL, a.pdl)
-        r.SetOption(api.OPT_GRAPH, a.graph)
+        if a.pdl >= 0:
+            r.SetOption(api.OPT_PDL, a.pdl)
+        if a.graph >= 0:
+            r.SetOption(api.OPT_GRAPH, a.graph)
         return r, time.perf_counter() - t0, broadcast_ms
 
     def timed(self, fn, steps):
@@ -782,8 +784,8 @@ def main():
     ap.add_argument("--sort-mode", default="lsd", choices=["binned", "lsd", "lsd_flat"])
     ap.add_argument("--sort-tile", type=int, default=0, choices=[0, 2048, 4096], help="onesweep tile: 0 = the library's automatic choice")
     ap.add_argument("--subblock-cull", type=int, default=2, choices=[0, 1, 2], help="compositor sub-block mask: 0 none, 1 box, 2 exact ellipse")
-    ap.add_argument("--graph", type=int, default=0, choices=[0, 1], help="replay a Sort's device work as one CUDA graph")
-    ap.add_argument("--pdl", type=int, default=0, choices=[0, 1], help="programmatic dependent launch of the frame's kernels (1 = default)")
+    ap.add_argument("--graph", type=int, default=-1, choices=[-1, 0, 1], help="replay a Sort's device work as one CUDA graph (-1: library default = on)")
+    ap.add_argument("--pdl", type=int, default=-1, help="programmatic dependent launch, mask: 1 depth passes, 2 emission, 4 tile passes, 8 compositor (-1: library default = 5)")
     ap.add_argument("--cpu-arm-child", action="store_true", help=argparse.SUPPRESS)
     ap.add_argument("--cpu-budget", type=float, default=150.0, help=argparse.SUPPRESS)
     ap.add_argument("--workload-json", default=None, help=argparse.SUPPRESS)

@@ -9,7 +9,9 @@ echo "gpu tests (parity, cull): exit $?"; tail -3 gpurun_out/gpu_tests.log
 i=0
 for args in "$@"; do
   for wl in 1m_deg0 6m_deg3_fp16; do
-    timeout 300 python bench.py --workload $wl --headline-only --no-parity --no-cpu-baseline --steps 30 --warmup 5 $args > gpurun_out/ab_${i}_$wl.json 2> gpurun_out/ab_${i}_$wl.err || tail -3 gpurun_out/ab_${i}_$wl.err
+    envs=""; opts=""
+    for tok in $args; do case "$tok" in [A-Z_]*=*) envs="$envs $tok";; *) opts="$opts $tok";; esac; done   # VAR=value tokens go to the environment
+    timeout 300 env $envs python bench.py --workload $wl --headline-only --no-parity --no-cpu-baseline --steps 30 --warmup 5 $opts > gpurun_out/ab_${i}_$wl.json 2> gpurun_out/ab_${i}_$wl.err || tail -3 gpurun_out/ab_${i}_$wl.err
     python - "$wl" "$args" gpurun_out/ab_${i}_$wl.json <<'PY'
 import json, sys
 wl, args, path = sys.argv[1:4]

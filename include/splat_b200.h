@@ -155,12 +155,14 @@ enum {
     SPL_OPT_SORT_MODE = 3,    /* SPL_SORT_LSD (default), SPL_SORT_LSD_FLAT or SPL_SORT_BINNED; all give bit-identical tile lists */
     SPL_OPT_SUBBLOCK_CULL = 5, /* compositor's per-entry 8x4 sub-block mask: 0 none, 1 footprint box, 2 exact ellipse (default);
                                  culling only skips lanes whose weight is discarded anyway: images are bit-identical */
-    SPL_OPT_GRAPH = 8,        /* 1: the device work of a Sort (control-block memset + projection + all sort passes) is captured and
-                                 replayed as ONE CUDA graph; the executable graph is updated in place every frame (the camera
-                                 changes the kernel arguments).  0 (default): individual launches.  Results are identical. */
-    SPL_OPT_PDL = 7,          /* 1 (default): the kernels of a frame are chained as programmatic dependent launches (a kernel's
-                                 prologue overlaps the tail of the one before it; griddepcontrol.wait guards every dependent
-                                 read).  0: plain stream order.  Results are identical. */
+    SPL_OPT_GRAPH = 8,        /* 1 (default): the device work of a Sort (control-block memset + projection + all sort passes) is
+                                 captured and replayed as ONE CUDA graph; the executable graph is updated in place every frame
+                                 (the camera changes the kernel arguments).  0: individual launches (also used automatically
+                                 while the caller is capturing the stream itself).  Results are identical. */
+    SPL_OPT_PDL = 7,          /* which kernels of a frame are launched as programmatic dependents of the kernel before them (a
+                                 kernel's prologue overlaps the predecessor's tail; griddepcontrol.wait guards every dependent
+                                 read): bit mask, 1 = depth passes, 2 = emission, 4 = tile passes, 8 = compositor.  Default 5
+                                 (measured best); 0 = plain stream order.  Results are identical. */
     SPL_OPT_SHARED_SORT = 6   /* what a Render does whose arguments differ from the last Sort's (the VR pattern: Sort for
                                  eye 0, Render for both eyes, src/app.cpp:603-607).  0 (default): sort again for the new
                                  view -- every image is exactly ordered.  1: the reference's behaviour -- keep the list and

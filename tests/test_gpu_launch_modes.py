@@ -37,7 +37,7 @@ def test_pdl_and_graph_are_bit_identical(splat, scratch, deg, n):
     cams = [scenes.translate(0, 0, 10.0), scenes.look_at_camera((6.0, 2.0, 7.0), (0, 0, 0)), scenes.translate(0.5, -0.5, 4.0)]
     base = _frames(splat, ply, {api.OPT_PDL: 0, api.OPT_GRAPH: 0}, cams, w, h)
     assert base[0][0][..., :3].max() > 0
-    for opts in ({api.OPT_PDL: 1, api.OPT_GRAPH: 0}, {api.OPT_PDL: 0, api.OPT_GRAPH: 1}, {api.OPT_PDL: 1, api.OPT_GRAPH: 1}):
+    for opts in ({api.OPT_PDL: 15, api.OPT_GRAPH: 0}, {api.OPT_PDL: 0, api.OPT_GRAPH: 1}, {api.OPT_PDL: 15, api.OPT_GRAPH: 1}, {api.OPT_PDL: 5, api.OPT_GRAPH: 1}):
         got = _frames(splat, ply, opts, cams, w, h)
         for (fb0, v0, r0), (fb1, v1, r1) in zip(base, got):
             np.testing.assert_array_equal(v0, v1, err_msg=str(opts))
@@ -53,7 +53,7 @@ def test_pdl_with_async_readback_and_other_paths(splat, scratch):
     for fmt in (api.FB_FP32, api.FB_FP16):
         for mode in (api.SORT_LSD, api.SORT_LSD_FLAT):
             base = _frames(splat, ply, {api.OPT_PDL: 0, api.OPT_GRAPH: 0}, cams, w, h, fmt, mode)
-            got = _frames(splat, ply, {api.OPT_PDL: 1, api.OPT_GRAPH: 1}, cams, w, h, fmt, mode)
+            got = _frames(splat, ply, {api.OPT_PDL: 15, api.OPT_GRAPH: 1}, cams, w, h, fmt, mode)
             for a, b in zip(base, got):
                 np.testing.assert_array_equal(a[0], b[0])
     proj = scenes.perspective(scenes.FOVY, w / h)
@@ -61,7 +61,7 @@ def test_pdl_with_async_readback_and_other_paths(splat, scratch):
     for pdl in (0, 1):
         r = splat.SplatRenderer()
         r.InitFromPly(ply, True, False)
-        r.SetOption(api.OPT_PDL, pdl)
+        r.SetOption(api.OPT_PDL, 15 * pdl)
         r.SetOption(api.OPT_GRAPH, pdl)
         r.SetOption(api.OPT_SHARED_SORT, 1)
         pin = [splat.host_alloc(w * h * 16), splat.host_alloc(w * h * 16)]
