@@ -485,6 +485,18 @@ def run_workload(rig: Rig, name: str, cam, steps: int, warmup: int, *, headline:
         fb_exact = r.ReadFramebuffer()
         r.SetOption(api.OPT_EARLY_OUT_T, EARLY_OUT_T)
 
+        launch_ms = None
+        if headline and rig.args.pdl < 0 and rig.args.graph < 0:
+            # ---- informational: what the launch mechanics are worth (same kernels, same results): plain stream order, the
+            # Sort replayed as one CUDA graph, and the default = graph + programmatic dependent launch of the sort passes
+            launch_ms = {}
+            for key, g, p in (("stream_order", 0, 0), ("graph", 1, 0), ("graph_pdl_default", 1, 5)):
+                r.SetOption(api.OPT_GRAPH, g)
+                r.SetOption(api.OPT_PDL, p)
+                launch_ms[key] = rig.timed(frame, steps)
+            launch_ms["saved_us_graph"] = (launch_ms["stream_order"] - launch_ms["graph"]) * 1e3
+            launch_ms["saved_us_graph_pdl"] = (launch_ms["stream_order"] - launch_ms["graph_pdl_default"]) * 1e3
+
         stereo_ms = None
         if headline:
             # ---- informational: the VR call pattern (src/app.cpp:603-607): Sort for the left eye, Render for both.  Default:
@@ -574,7 +586,7 @@ def run_workload(rig: Rig, name: str, cam, steps: int, warmup: int, *, headline:
         "load_s": load_s, "broadcast_ms": broadcast_ms, "fp16_target": w["fp16"],
     })
     res["_internal"] = {"stages": stages, "ab": ab, "cand": cand, "launches": launches, "wall": wall, "clocks": clocks.summary() if clocks else None,
-                        "e2e8_ms": e2e8_ms, "stereo_ms": stereo_ms, "n": n}
+                        "e2e8_ms": e2e8_ms, "stereo_ms": stereo_ms, "launch_ms": launch_ms, "n": n}
     return res
 
 
@@ -678,6 +690,7 @@ def run_ours(args, rank, local_rank, world):
         "e2e_presented_rgba8": {"value": n * steps * world / (e2e8_ms * 1e-3) / 1e6, "unit": "Msplats/s", "d2h_bytes_per_step": WIDTH * HEIGHT * 4,
                                 "ms_per_step": e2e8_ms / steps,
                                 "note": "informational: same loop, reading the 8-bit presented frame (RenderDesktop blit) instead of the float target"},
+        "launch_modes": it["launch_ms"],
         "gpu_launches": it["launches"] * steps,
         "roofline": main_roof,
         "stage_ms": main["stage_ms"], "stage_gbs": main["stage_gbs"],
