@@ -117,7 +117,7 @@ struct CompSmem
 template <bool HALF>
 __global__ void __launch_bounds__(kCompThreads, 5)
 k_composite(const uint2* ranges, const uint32_t* vals, int idStride, const ProjRecord* rec,
-            void* __restrict__ fb, int width, int height, int tilesX, int tileBitsX, float earlyOutT, int cullMode, uint32_t beginXor, FrameReport report)
+            void* __restrict__ fb, int width, int height, int tilesX, float earlyOutT, int cullMode, uint32_t beginXor, FrameReport report)
 {
     __shared__ CompSmem s;
     pdl_wait();  // tile ranges, sorted ids and records are the preceding kernels' output (no-op in a normal launch)
@@ -145,8 +145,7 @@ k_composite(const uint2* ranges, const uint32_t* vals, int idStride, const ProjR
     const float pu = ((float)x + 0.5f) - tileCx;
     const f32x2 pv = pack2(((float)y0 + 0.5f) - tileCy, ((float)y1 + 0.5f) - tileCy);
 
-    // default path: the ranges are indexed by the instance key (tile row << tileBitsX | tile column), else by the tile number
-    uint2 range = ranges[tileBitsX >= 0 ? ((tileY << tileBitsX) | tileX) : tile];
+    uint2 range = ranges[tile];
     range.x ^= beginXor;  // ranges written by the last sort pass store ~begin (kernels.h: SortWorkspace::tileRanges)
     // T == 0 marks a finished pixel: every later contribution is multiplied by it
     f32x2 T = pack2(inside0 ? 1.0f : 0.0f, inside1 ? 1.0f : 0.0f);
@@ -431,16 +430,16 @@ cudaError_t launch_present_rgba8(const void* framebuffer, int fbFormat, uint32_t
 }
 
 cudaError_t launch_composite(const uint2* ranges, const uint32_t* sortedVals, int idStrideWords, const ProjRecord* rec, void* framebuffer,
-                             int fbFormat, int width, int height, int tilesX, int tilesY, int tileBitsX, float earlyOutT, int cullMode, uint32_t rangeBeginXor,
+                             int fbFormat, int width, int height, int tilesX, int tilesY, float earlyOutT, int cullMode, uint32_t rangeBeginXor,
                              const FrameReport& report, cudaStream_t stream, bool pdl)
 {
     const int tiles = tilesX * tilesY;
     if (tiles <= 0) return cudaSuccess;
     if (fbFormat == 1)
         return launch_kernel(k_composite<true>, dim3(tiles), dim3(kCompThreads), 0, stream, pdl, ranges, sortedVals, idStrideWords, rec, framebuffer, width, height, tilesX,
-                             tileBitsX, earlyOutT, cullMode, rangeBeginXor, report);
+                             earlyOutT, cullMode, rangeBeginXor, report);
     return launch_kernel(k_composite<false>, dim3(tiles), dim3(kCompThreads), 0, stream, pdl, ranges, sortedVals, idStrideWords, rec, framebuffer, width, height, tilesX,
-                         tileBitsX, earlyOutT, cullMode, rangeBeginXor, report);
+                         earlyOutT, cullMode, rangeBeginXor, report);
 }
 
 }  // namespace splat

@@ -28,13 +28,6 @@ constexpr uint32_t kSortGenerationMask = 31;
 
 constexpr uint64_t kMaxInstances = (1ull << 30) - 1;  // tile instances one frame may hold
 
-// default path: the instance key (tile row << bitsX | tile column) is sorted in 8-bit digits that do not straddle the two
-// coordinates: ceil(bitsX / 8) column passes (at least one, so that a pass exists which creates the instances), then
-// ceil(bitsY / 8) row passes -- at most kMaxTileDigits
-constexpr int kMaxTileDigits = 4;
-__host__ __device__ __forceinline__ int tile_x_passes(int bitsX) { return bitsX > kRadixBits ? 2 : 1; }
-__host__ __device__ __forceinline__ int tile_y_passes(int bitsY) { return bitsY == 0 ? 0 : (bitsY > kRadixBits ? 2 : 1); }
-
 // per-tile segment sort (binsort.cu): segments up to kSegSortSmallCap are sorted by a 256-thread CTA in 2 x 16 KiB
 // of static shared memory, up to kSegSortLargeCap by a 1024-thread CTA in 2 x 96 KiB, longer ones through global memory
 constexpr int kSegSortSmallCap = 2048;
@@ -52,9 +45,6 @@ struct FrameConstants
     float eye[3];
     float W, H, zNear, zFar;
     int width, height, tilesX, tilesY;
-    // default path: an instance's sort key is (tile row << tileBitsX) | tile column -- the column and the row are sorted as
-    // separate digits, whose histograms are sums over a rectangle's columns / rows (k_project_keys)
-    int tileBitsX, tileBitsY;
     int srgb;
     // shared sort (the reference's VR path sorts for eye 0 and draws both eyes in that order, src/app.cpp:603-607):
     float zFarSort;   // far plane of the Sort call (= zFar unless a Render re-projects for another eye)
@@ -100,7 +90,6 @@ struct FrameCounters
     unsigned int sortTickets[kMaxSortPasses];
     unsigned int largeTiles;            // tiles whose segment exceeds kSegSortSmallCap (binned sort)
     unsigned int sortCount;             // elements of the per-gaussian depth sort (default LSD path): N
-    unsigned int lastExpandEntry;       // default path: index (in depth order) of the last entry that has tile instances
 };
 
 // ---------------------------------------------------------------------------------------------------

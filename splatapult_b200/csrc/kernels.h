@@ -42,14 +42,13 @@ cudaError_t launch_project(const PackedCloud& cloud, const FrameConstants& fc, P
 // default LSD path: (1) project + one (u32 depthKey, id) pair and an 8-byte tile rectangle per gaussian; after the
 // depth digits have been sorted on those N pairs, (2) expand the sorted id list into (u32 tile id, id) instances in
 // depth order (scan + coalesced emission) and leave the histogram of the first tile digit in tileDigitHist
-// tileHist: kMaxTileDigits x 256 counters, the histograms of the instance key's digits (tile column digits, then row digits)
 cudaError_t launch_project_keys(const PackedCloud& cloud, const FrameConstants& fc, ProjRecord* rec, uint32_t* keys, uint32_t* vals,
-                                uint2* side, FrameCounters* ctr, uint32_t* digit0Hist, uint32_t* tileHist, cudaStream_t stream);
-// (2) scan of the depth-sorted list: per entry the offset of its first tile instance and its packed rectangle (x0 | y0 << 10 |
-// (w - 1) << 20), per sort tile (sortTileKeys instances) of the first tile-digit pass the entry holding its first instance;
-// ctr->usedInstances / totalInstances / lastExpandEntry.  The instances themselves are created by that sort pass (ExpandSource).
-cudaError_t launch_expand_scan(const uint32_t* sortedVals, const uint2* side, uint32_t n, uint32_t* expOff, uint32_t* expRect, uint32_t* tileStart,
-                               uint32_t sortTileKeys, FrameCounters* ctr, unsigned long long* scanState, uint32_t capacity, cudaStream_t stream, bool pdl = false);
+                                uint2* side, FrameCounters* ctr, uint32_t* digit0Hist, cudaStream_t stream);
+// tileDigitHist: 2 x 256 counters, the histograms of BOTH tile digits (bits 0-7 and 8-15 of the tile id).  pdl: launch as a
+// programmatic dependent of the preceding kernel (the last depth pass)
+cudaError_t launch_emit_sorted(const uint32_t* sortedVals, const uint2* side, uint32_t n,
+                               const FrameConstants& fc, uint32_t* keys, uint32_t* vals, FrameCounters* ctr,
+                               unsigned long long* scanState, uint32_t capacity, uint32_t* tileDigitHist, cudaStream_t stream, bool pdl = false);
 
 cudaError_t launch_project_bin(const PackedCloud& cloud, const FrameConstants& fc, ProjRecord* rec, uint4* side, uint32_t* tileCount,
                                FrameCounters* ctr, cudaStream_t stream);
@@ -64,19 +63,6 @@ cudaError_t launch_segment_sort(unsigned long long* pairs, unsigned long long* s
                                 const uint32_t* largeList, const FrameCounters* ctr, int numSMs, cudaStream_t stream);
 
 // ---- radix_sort.cu : device-wide LSD radix sort of (u64 key, u32 value) pairs, 8-bit digits, onesweep style
-// what the FIRST pass of the instance sort creates its input from (default path): entry j of the depth-sorted list owns the
-// instances [off[j], off[j + 1]) -- the last entry up to the instance count --, tile (x0 + c, y0 + r) in row-major order of its
-// rectangle; key = (row << tileBitsX) | column, payload = ids[j]
-struct ExpandSource
-{
-    const uint32_t* off = nullptr;        // null: the pass reads its keys like every other pass
-    const uint32_t* rect = nullptr;       // x0 | y0 << 10 | (w - 1) << 20
-    const uint32_t* ids = nullptr;
-    const uint32_t* tileStart = nullptr;  // per sort tile of this pass: the entry holding its first instance
-    const uint32_t* lastEntry = nullptr;  // device word: the last entry that has instances
-    int tileBitsX = 0;
-};
-
 struct SortWorkspace
 {
     uint32_t* histograms;         // [kMaxSortPasses][256] global digit counts; a sort's first row is filled by its producer,
@@ -103,12 +89,6 @@ struct SortWorkspace
     // launch every pass as a programmatic dependent of the kernel before it (device_common.cuh: pdl_wait); the first pass
     // then assumes that its histogram row comes from that kernel, later passes only when allHistogramsReady is false
     bool pdl = false;
-    // optional explicit digit list (shift, bits) instead of 8-bit digits from beginBit: the default path's instance key is
-    // sorted column digits first, then row digits (device_common.cuh: tile_x_passes)
-    int numCustomPasses = 0;
-    int customShift[kMaxTileDigits] = {};
-    int customBits[kMaxTileDigits] = {};
-    ExpandSource expand;  // pass 0 creates its keys from this instead of reading them
 };
 size_t sort_group_words(uint64_t capacity, int keysPerThread);
 constexpr uint32_t kFusedRangeBeginXor = 0xFFFFFFFFu;  // begin = ranges[t].x ^ this
@@ -136,8 +116,7 @@ cudaError_t launch_sort_passes32(uint32_t* keysA, uint32_t* valsA, uint32_t* key
 cudaError_t launch_tile_ranges(const void* sortedKeys, int keyBytes, const uint32_t* nDevice, uint64_t capacity, uint2* ranges,
                                uint32_t numTiles, int numSMs, cudaStream_t stream);
 // ids: gaussian id of list entry k is ids[k * idStrideWords] (1: u32 payload array of the LSD sort, 2: low word of the
-// binned sort's u64 (depthKey << 32 | id) pairs); tileBitsX >= 0: ranges are indexed by (tile row << tileBitsX | tile column)
-// (default path), -1: by the tile number
+// binned sort's u64 (depthKey << 32 | id) pairs)
 // report: where the frame's instance count is posted for the host (mapped pinned memory; hostWord null = no report)
 struct FrameReport
 {
@@ -148,7 +127,7 @@ struct FrameReport
 constexpr int kReportSeqShift = 40;
 constexpr unsigned long long kReportCountMask = (1ull << kReportSeqShift) - 1;
 cudaError_t launch_composite(const uint2* ranges, const uint32_t* ids, int idStrideWords, const ProjRecord* rec, void* framebuffer, int fbFormat,
-                             int width, int height, int tilesX, int tilesY, int tileBitsX, float earlyOutT, int cullMode, uint32_t rangeBeginXor,
+                             int width, int height, int tilesX, int tilesY, float earlyOutT, int cullMode, uint32_t rangeBeginXor,
                              const FrameReport& report, cudaStream_t stream, bool pdl = false);
 
 // float target -> packed RGBA8 (R in the low byte), same pixel order as the target

@@ -443,44 +443,46 @@ k_project(const PackedCloud cloud, const __grid_constant__ FrameConstants fc, Pr
 }
 
 // ---------------------------------------------------------------------------------------------------
-// default LSD path, step 2: scan of the depth-sorted gaussian list.  Entry j (the j-th gaussian in depth order) will expand to
-// count_j = w x h tile instances; this kernel leaves, per entry, the offset of its first instance (exclusive prefix of the
-// counts: block scan + single-pass decoupled look-back over CTA aggregates, dynamic CTA ids) and its packed rectangle, and per
-// sort tile of the FIRST tile-digit pass the entry that holds that tile's first instance.  The instances themselves are never
-// written by anybody: the first tile-digit pass of the sorter generates its 4096 (or 2048) of them straight into its
-// shared-memory tile (radix_sort.cu, EXPAND) -- the 8 D bytes of emission output and their re-read are gone, and so is the
-// emission loop (round 1: k_emit_sorted, 35 us at 1 M, 117 us at 6 M gaussians).
-// Every thread carries kEmitRounds entries (entry j = cta * 1024 + round * 256 + tid): a quarter of the CTAs means a quarter of
-// the links in the look-back chain.  D never leaves the device.
+// default LSD path, step 2: expand the depth-sorted gaussian list into (tile id, gaussian id) instances, in depth
+// order -- the instances do not carry the depth key: the tile-digit passes that follow are stable.  Same scan + look-back + warp-cooperative emission as k_project, but every thread carries
+// kEmitRounds entries (entry j = cta * 1024 + round * 256 + tid, so loads stay coalesced and the emission order is
+// the list order): a quarter of the CTAs means a quarter of the links in the look-back chain.  With one entry per
+// thread the walkers (32 predecessors per L2 round trip) were slower than the rate at which new CTAs start, so the
+// walks kept growing and 7 of 8 warps sat on the barrier behind warp 0 (ncu: barrier stall 21 warps per issue).
 // ---------------------------------------------------------------------------------------------------
 constexpr int kEmitRounds = 4;
 
 __global__ void __launch_bounds__(kProjThreads)
-k_expand_scan(const uint32_t* sortedVals, const uint2* side, uint32_t nSorted, uint32_t* __restrict__ expOff, uint32_t* __restrict__ expRect,
-              uint32_t* __restrict__ tileStart, uint32_t sortTileKeys, FrameCounters* __restrict__ ctr, unsigned long long* __restrict__ scanState,
-              uint32_t capacity)
+k_emit_sorted(const uint32_t* sortedVals, const uint2* side,
+              uint32_t nSorted, uint32_t tilesX, uint32_t* __restrict__ keys, uint32_t* __restrict__ vals,
+              FrameCounters* __restrict__ ctr, unsigned long long* __restrict__ scanState, uint32_t capacity, uint32_t* __restrict__ tileDigitHist)
 {
     constexpr int kWarps = kProjThreads / 32;
     __shared__ uint32_t sBlockId;
     __shared__ uint32_t sWarpTotal[kEmitRounds][kWarps];
     __shared__ unsigned long long sBlockBase;
+    __shared__ uint32_t sDigit0[2][kRadixSize];  // histograms of both tile digits (bits 0-7 and 8-15 of the tile id), one count per instance
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid == 0) sBlockId = atomicAdd(&ctr->projectTicket, 1u);  // dynamic id: predecessors are resident or done
-    pdl_wait();  // the depth-sorted list is the last depth pass's output (no-op in a normal launch)
+    sDigit0[0][tid] = 0;
+    sDigit0[1][tid] = 0;
+    pdl_wait();     // the depth-sorted list is the last depth pass's output
+    pdl_trigger();  // the first tile pass may be scheduled as this grid retires
     __syncthreads();
     const uint32_t vbid = sBlockId;
 
-    uint32_t count[kEmitRounds], rect[kEmitRounds], incl[kEmitRounds];
+    uint32_t count[kEmitRounds], rect[kEmitRounds], id[kEmitRounds], incl[kEmitRounds];
 #pragma unroll
     for (int r = 0; r < kEmitRounds; r++)
     {
         const uint32_t j = (vbid * kEmitRounds + r) * kProjThreads + tid;
-        count[r] = 0; rect[r] = 0;
+        count[r] = 0; rect[r] = 0; id[r] = 0;
         if (j < nSorted)
         {
             // plain loads, not the read-only path (__ldg): ptxas is free to move LDG.CONSTANT loads above pdl_wait()
-            const uint2 sd = side[sortedVals[j]];
+            id[r] = sortedVals[j];
+            const uint2 sd = side[id[r]];
             const uint32_t w = sd.y & 0xffffu, h = sd.y >> 16;
             count[r] = w * h;
             rect[r] = (sd.x & 0xffffu) | ((sd.x >> 16) << 10) | ((w ? w - 1 : 0) << 20);
@@ -553,54 +555,79 @@ k_expand_scan(const uint32_t* sortedVals, const uint2* side, uint32_t nSorted, u
     }
     __syncthreads();
 
-    // ---- per entry: offset, rectangle; per sort tile: the entry that holds its first instance
+    // ---- warp-cooperative, coalesced emission, one round at a time
+    // (measured alternatives, round 2: every lane writing its own entry's instances serially -- a third of the instructions,
+    // but scattered partial-sector stores: 103 vs 99 us for sort+emit at 1 M, 302 vs 316 at 6 M; the same with the warp's run
+    // staged in shared memory and copied out coalesced: 110 / 323 us.  The kernel's time is its scan chain, not the emission.)
     const unsigned long long blockBase = sBlockBase;
-    uint32_t usedEnd = 0, lastEntry = 0;
+    uint32_t usedEnd = 0;
 #pragma unroll
     for (int r = 0; r < kEmitRounds; r++)
     {
-        const uint32_t j = (vbid * kEmitRounds + r) * kProjThreads + tid;
-        if (j >= nSorted) continue;
         const unsigned long long gOff64 = blockBase + base[r] + (incl[r] - count[r]);
         const bool fits = gOff64 + count[r] <= (unsigned long long)capacity;
+        const uint32_t cntE = fits ? count[r] : 0u;
         if (!fits) atomicOr(&ctr->overflow, 1u);
-        // entries that do not fit are a suffix of the list: their (clamped) offsets are >= usedInstances and expand to nothing
-        const uint32_t gOff = (uint32_t)(gOff64 < (unsigned long long)capacity ? gOff64 : (unsigned long long)capacity);
-        expOff[j] = gOff;
-        expRect[j] = rect[r];
-        if (fits && count[r])
+        const uint32_t gOff = fits ? (uint32_t)gOff64 : 0u;
+        if (cntE) usedEnd = max(usedEnd, gOff + cntE);
+
+        uint32_t inclE = cntE;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1)
         {
-            usedEnd = max(usedEnd, gOff + count[r]);
-            lastEntry = max(lastEntry, j);
-            const uint32_t tFirst = (gOff + sortTileKeys - 1) / sortTileKeys, tLast = (gOff + count[r] - 1) / sortTileKeys;
-            for (uint32_t t = tFirst; t <= tLast; t++) tileStart[t] = j;  // instance t * sortTileKeys lies in this entry
+            const uint32_t v = __shfl_up_sync(0xffffffffu, inclE, d);
+            if (lane >= d) inclE += v;
+        }
+        const uint32_t wexE = inclE - cntE;
+        const uint32_t T = __shfl_sync(0xffffffffu, inclE, 31);
+        for (uint32_t j0 = 0; j0 < T; j0 += 32)
+        {
+            const uint32_t j = j0 + lane;
+            int owner = 0;
+#pragma unroll
+            for (int s = 16; s; s >>= 1)
+            {
+                const int cand = owner + s;
+                const uint32_t v = __shfl_sync(0xffffffffu, wexE, cand);
+                if (v <= j) owner = cand;
+            }
+            const uint32_t oBase = __shfl_sync(0xffffffffu, wexE, owner);
+            const uint32_t oOff = __shfl_sync(0xffffffffu, gOff, owner);
+            const uint32_t oRect = __shfl_sync(0xffffffffu, rect[r], owner);
+            const uint32_t oId = __shfl_sync(0xffffffffu, id[r], owner);
+            if (j < T)
+            {
+                const uint32_t k = j - oBase;
+                const uint32_t w = (oRect >> 20) + 1, x0 = oRect & 1023u, y0 = (oRect >> 10) & 1023u;
+                const uint32_t row = k / w, col = k - row * w;
+                const uint32_t tile = (y0 + row) * tilesX + (x0 + col);
+                keys[oOff + k] = tile;
+                vals[oOff + k] = oId;
+                if (tileDigitHist)
+                {
+                    smem_red_add(&sDigit0[0][tile & (kRadixSize - 1)], 1u);
+                    smem_red_add(&sDigit0[1][(tile >> kRadixBits) & (kRadixSize - 1)], 1u);
+                }
+            }
         }
     }
 #pragma unroll
-    for (int d = 16; d; d >>= 1)
-    {
-        usedEnd = max(usedEnd, __shfl_xor_sync(0xffffffffu, usedEnd, d));
-        lastEntry = max(lastEntry, __shfl_xor_sync(0xffffffffu, lastEntry, d));
-    }
-    // one atomic per CTA on each frame counter, not one per warp: same-address atomics serialise in L2
-    __shared__ uint32_t sLast[kWarps];
-    if (lane == 0)
-    {
-        sWarpTotal[0][warp] = usedEnd;  // sWarpTotal is free again: every warp passed the barrier after the scan
-        sLast[warp] = lastEntry;
-    }
+    for (int d = 16; d; d >>= 1) usedEnd = max(usedEnd, __shfl_xor_sync(0xffffffffu, usedEnd, d));
+    // one atomic per CTA on the frame counter, not one per warp: same-address atomics serialise in L2
+    if (lane == 0) sWarpTotal[0][warp] = usedEnd;  // sWarpTotal is free again: every warp passed the barrier after the scan
     __syncthreads();
     if (tid == 0)
     {
-        uint32_t m = 0, l = 0;
+        uint32_t m = 0;
 #pragma unroll
-        for (int w = 0; w < kWarps; w++)
-        {
-            m = max(m, sWarpTotal[0][w]);
-            l = max(l, sLast[w]);
-        }
+        for (int w = 0; w < kWarps; w++) m = max(m, sWarpTotal[0][w]);
         if (m) atomicMax(&ctr->usedInstances, m);
-        if (l) atomicMax(&ctr->lastExpandEntry, l);
+    }
+    if (tileDigitHist)
+    {
+        const uint32_t c0 = sDigit0[0][tid], c1 = sDigit0[1][tid];
+        if (c0) atomicAdd(tileDigitHist + tid, c0);
+        if (c1) atomicAdd(tileDigitHist + kRadixSize + tid, c1);
     }
 }
 
@@ -613,7 +640,7 @@ template <int SH_MODE>
 __global__ void __launch_bounds__(kProjThreads)
 k_project_keys(const PackedCloud cloud, const __grid_constant__ FrameConstants fc, ProjRecord* __restrict__ rec,
                uint32_t* __restrict__ keys, uint32_t* __restrict__ vals, uint2* __restrict__ side, FrameCounters* __restrict__ ctr,
-               uint32_t* __restrict__ digit0Hist, uint32_t* __restrict__ tileHist)
+               uint32_t* __restrict__ digit0Hist)
 {
     // grid-stride over chunks of 256 gaussians: the CTA keeps its digit histogram and its visible count across chunks
     // and flushes them once.  (With one CTA per chunk and one atomicAdd per warp on ctr->visible, that single L2
@@ -621,19 +648,11 @@ k_project_keys(const PackedCloud cloud, const __grid_constant__ FrameConstants f
     // histograms of ALL FOUR depth digits: the keys are in registers here, so the depth passes of the sorter neither need a
     // histogram pass nor accumulate the next digit's histogram while they scatter
     __shared__ uint32_t sDigit[kDepthBits / kRadixBits][kRadixSize];
-    // ... and of the tile digits of the instances the gaussians will expand to.  An instance's key is (tile row << tileBitsX) |
-    // tile column, sorted one coordinate at a time: the histogram of a column digit is "for every column of the rectangle,
-    // += its height", that of a row digit "for every row, += its width" -- w + h updates per gaussian instead of w x h, so
-    // nobody has to enumerate the instances before the sort pass that creates them (radix_sort.cu: EXPAND)
-    __shared__ uint32_t sTile[kMaxTileDigits][kRadixSize];
-    const int nXp = tile_x_passes(fc.tileBitsX), nYp = tile_y_passes(fc.tileBitsY);
     const int tid = threadIdx.x;
     pdl_trigger();  // first kernel of the frame's chain (launched normally, after the control-block memset): the first depth
                     // pass may be scheduled as this grid's CTAs retire; it waits for this grid before it reads anything
 #pragma unroll
     for (int p = 0; p < kDepthBits / kRadixBits; p++) sDigit[p][tid] = 0;
-#pragma unroll
-    for (int p = 0; p < kMaxTileDigits; p++) sTile[p][tid] = 0;
     __syncthreads();
     uint32_t visibleMine = 0;
     const uint32_t numChunks = (cloud.n + kProjThreads - 1) / kProjThreads;
@@ -645,21 +664,6 @@ k_project_keys(const PackedCloud cloud, const __grid_constant__ FrameConstants f
         if (inRange)
         {
             side[i] = pg.count ? make_uint2(pg.x0 | (pg.y0 << 16), pg.w | (pg.h << 16)) : make_uint2(0u, 0u);
-            if (pg.count && tileHist)
-            {
-                for (uint32_t c = 0; c < pg.w; c++)
-                {
-                    const uint32_t tx = pg.x0 + c;
-                    smem_red_add(&sTile[0][tx & (kRadixSize - 1)], pg.h);
-                    if (nXp > 1) smem_red_add(&sTile[1][(tx >> kRadixBits) & (kRadixSize - 1)], pg.h);
-                }
-                for (uint32_t r = 0; r < pg.h && nYp > 0; r++)
-                {
-                    const uint32_t ty = pg.y0 + r;
-                    smem_red_add(&sTile[nXp][ty & (kRadixSize - 1)], pg.w);
-                    if (nYp > 1) smem_red_add(&sTile[nXp + 1][(ty >> kRadixBits) & (kRadixSize - 1)], pg.w);
-                }
-            }
             if (fc.stereoPass != 2)
             {
                 // shared sort: the order must hold for an eye that may draw what this one does not
@@ -688,14 +692,6 @@ k_project_keys(const PackedCloud cloud, const __grid_constant__ FrameConstants f
     {
         const uint32_t c = sDigit[p][tid];
         if (c) atomicAdd(digit0Hist + p * kRadixSize + tid, c);  // all zero in a render-only pass
-    }
-    if (tileHist)
-    {
-        for (int p = 0; p < nXp + nYp; p++)
-        {
-            const uint32_t c = sTile[p][tid];
-            if (c) atomicAdd(tileHist + p * kRadixSize + tid, c);
-        }
     }
 }
 
@@ -857,7 +853,7 @@ cudaError_t launch_project(const PackedCloud& cloud, const FrameConstants& fc, P
 }
 
 cudaError_t launch_project_keys(const PackedCloud& cloud, const FrameConstants& fc, ProjRecord* rec, uint32_t* keys, uint32_t* vals,
-                                uint2* side, FrameCounters* ctr, uint32_t* digit0Hist, uint32_t* tileHist, cudaStream_t stream)
+                                uint2* side, FrameCounters* ctr, uint32_t* digit0Hist, cudaStream_t stream)
 {
     uint32_t blocks = project_num_blocks(cloud.n);
     if (blocks == 0) return cudaSuccess;
@@ -892,21 +888,22 @@ cudaError_t launch_project_keys(const PackedCloud& cloud, const FrameConstants& 
     blocks = min(blocks, (uint32_t)(ctasPerWave[mode] * waves));
     switch (cloud.shMode)
     {
-    case 0: k_project_keys<0><<<blocks, kProjThreads, 0, stream>>>(cloud, fc, rec, keys, vals, side, ctr, digit0Hist, tileHist); break;
-    case 1: k_project_keys<1><<<blocks, kProjThreads, 0, stream>>>(cloud, fc, rec, keys, vals, side, ctr, digit0Hist, tileHist); break;
-    default: k_project_keys<3><<<blocks, kProjThreads, 0, stream>>>(cloud, fc, rec, keys, vals, side, ctr, digit0Hist, tileHist); break;
+    case 0: k_project_keys<0><<<blocks, kProjThreads, 0, stream>>>(cloud, fc, rec, keys, vals, side, ctr, digit0Hist); break;
+    case 1: k_project_keys<1><<<blocks, kProjThreads, 0, stream>>>(cloud, fc, rec, keys, vals, side, ctr, digit0Hist); break;
+    default: k_project_keys<3><<<blocks, kProjThreads, 0, stream>>>(cloud, fc, rec, keys, vals, side, ctr, digit0Hist); break;
     }
     return cudaGetLastError();
 }
 
-cudaError_t launch_expand_scan(const uint32_t* sortedVals, const uint2* side, uint32_t n, uint32_t* expOff, uint32_t* expRect, uint32_t* tileStart,
-                               uint32_t sortTileKeys, FrameCounters* ctr, unsigned long long* scanState, uint32_t capacity, cudaStream_t stream, bool pdl)
+cudaError_t launch_emit_sorted(const uint32_t* sortedVals, const uint2* side, uint32_t n,
+                               const FrameConstants& fc, uint32_t* keys, uint32_t* vals, FrameCounters* ctr,
+                               unsigned long long* scanState, uint32_t capacity, uint32_t* tileDigitHist, cudaStream_t stream, bool pdl)
 {
     const uint32_t perCta = kProjThreads * kEmitRounds;
     const uint32_t blocks = (n + perCta - 1) / perCta;  // <= project_num_blocks(n): scanState is large enough
     if (blocks == 0) return cudaSuccess;
-    return launch_kernel(k_expand_scan, dim3(blocks), dim3(kProjThreads), 0, stream, pdl, sortedVals, side, n, expOff, expRect, tileStart, sortTileKeys, ctr, scanState,
-                         capacity);
+    return launch_kernel(k_emit_sorted, dim3(blocks), dim3(kProjThreads), 0, stream, pdl, sortedVals, side, n, (uint32_t)fc.tilesX, keys, vals, ctr, scanState,
+                         capacity, tileDigitHist);
 }
 
 uint32_t project_num_blocks(uint32_t n) { return (n + kProjThreads - 1) / kProjThreads; }

@@ -134,9 +134,6 @@ k_sort_histogram(const unsigned long long* __restrict__ keys, const uint32_t* __
 // ---------------------------------------------------------------------------------------------------
 // KeyT = unsigned long long (tile << 32 | depthKey, and the stand-alone sorter) or uint32_t (the frame's depth keys on
 // the gaussians and bare tile ids on the instances: 8 bytes per element instead of 12, 4 CTAs per SM instead of 3)
-constexpr uint32_t kExpandSerialMax = 24;  // an entry with at most this many instances in the tile is written by one thread
-constexpr uint32_t kExpandBigCap = 256;    // > 4096 / kExpandSerialMax: larger entries of one tile always fit the list
-
 template <int KPT, typename KeyT>
 struct SortSmem
 {
@@ -152,8 +149,6 @@ struct SortSmem
     uint32_t scanTmp[kWarps];
     float sqTmp[kWarps];
     uint32_t tile;
-    uint32_t bigCount;                            // EXPAND: entries of this tile that are expanded by the whole CTA ...
-    uint32_t bigList[kExpandBigCap];              // ... (more than kExpandSerialMax instances inside the tile)
     uint64_t bar;
 };
 
@@ -175,15 +170,13 @@ struct SortSmem
 #define TLREC(k) ((void)0)
 #endif
 
-// EXPAND (u32 keys, first pass of the default path's instance sort): the tile is not read but CREATED in shared memory from
-// the scan of the depth-sorted gaussian list (ExpandSource): nobody ever writes the unsorted instances to global memory.
-template <int KPT, typename KeyT, bool EXPAND = false>
+template <int KPT, typename KeyT>
 __global__ void __launch_bounds__(kSortThreads, KPT == 16 ? (sizeof(KeyT) == 4 ? 4 : 3) : 5)
 k_sort_onesweep(const KeyT* __restrict__ keysIn, const uint32_t* __restrict__ valsIn, KeyT* __restrict__ keysOut,
                 uint32_t* __restrict__ valsOut, const uint32_t* nDevice, int shift, uint32_t mask, int nextShift, uint32_t nextMask,
                 const uint32_t* histogram, uint32_t* __restrict__ histogramNext, unsigned long long* __restrict__ status,
                 uint32_t* __restrict__ ticket, uint32_t gen, unsigned long long* tl, uint2* __restrict__ tileRanges, uint32_t numRangeTiles,
-                uint32_t statusTiles, int rangeShift, unsigned long long* __restrict__ groupAgg, int histFromPredecessor, const ExpandSource expand)
+                uint32_t statusTiles, int rangeShift, unsigned long long* __restrict__ groupAgg, int histFromPredecessor)
 {
     using Smem = SortSmem<KPT, KeyT>;
     constexpr int kTile = Smem::kTile;
@@ -231,7 +224,6 @@ k_sort_onesweep(const KeyT* __restrict__ keysIn, const uint32_t* __restrict__ va
         {
             mbar_init(&s.bar, 1);
             mbar_fence_init();
-            s.bigCount = 0;
         }
         __syncthreads();
         uint32_t base = 0;
@@ -261,72 +253,16 @@ k_sort_onesweep(const KeyT* __restrict__ keysIn, const uint32_t* __restrict__ va
         const uint32_t nValid = min((uint32_t)kTile, n - tile * kTile);
         TLREC(0);
 
-        if (EXPAND)
+        if (tid == 0)
         {
-            // create the tile: entries [jLo, jHi] of the depth-sorted list own its instances [base, base + nValid)
-            const uint32_t base = tile * kTile;
-            const uint32_t jLast = expand.lastEntry[0];
-            const uint32_t jLo = expand.tileStart[tile], jHi = tile + 1 < numTiles ? expand.tileStart[tile + 1] : jLast;
-            const uint32_t bitsX = (uint32_t)expand.tileBitsX;
-            for (uint32_t j = jLo + tid; j <= jHi; j += kSortThreads)
-            {
-                const uint32_t off = expand.off[j], end = j == jLast ? n : expand.off[j + 1];
-                const uint32_t lo = max(off, base), hi = min(end, base + nValid);
-                if (hi <= lo) continue;  // no instance in this tile (count 0, or the entries of a neighbour tile)
-                if (hi - lo > kExpandSerialMax)
-                {
-                    const uint32_t slot = atomicAdd(&s.bigCount, 1u);
-                    s.bigList[slot] = j;  // at most kTile / (kExpandSerialMax + 1) < kExpandBigCap of them
-                    continue;
-                }
-                const uint32_t rect = expand.rect[j], id = expand.ids[j];
-                const uint32_t w = (rect >> 20) + 1, x0 = rect & 1023u, y0 = (rect >> 10) & 1023u;
-                const uint32_t k0 = lo - off;  // first instance of the entry inside the tile; instances are row-major
-                uint32_t row = k0 / w, col = k0 - row * w;
-                for (uint32_t i = lo - base; i < hi - base; i++)
-                {
-                    s.keys[i] = (KeyT)(((y0 + row) << bitsX) | (x0 + col));
-                    s.vals[i] = id;
-                    if (++col == w)
-                    {
-                        col = 0;
-                        row++;
-                    }
-                }
-            }
-            __syncthreads();
-            // entries with many instances in the tile (large or close splats): the whole CTA, one entry at a time
-            const uint32_t nBig = s.bigCount;
-            for (uint32_t b = 0; b < nBig; b++)
-            {
-                const uint32_t j = s.bigList[b];
-                const uint32_t off = expand.off[j], end = j == jLast ? n : expand.off[j + 1];
-                const uint32_t lo = max(off, base), hi = min(end, base + nValid);
-                const uint32_t rect = expand.rect[j], id = expand.ids[j];
-                const uint32_t w = (rect >> 20) + 1, x0 = rect & 1023u, y0 = (rect >> 10) & 1023u;
-                for (uint32_t i = lo + tid; i < hi; i += kSortThreads)
-                {
-                    const uint32_t k = i - off, row = k / w, col = k - row * w;
-                    s.keys[i - base] = (KeyT)(((y0 + row) << bitsX) | (x0 + col));
-                    s.vals[i - base] = id;
-                }
-            }
-            __syncthreads();
-            if (tid == 0) s.bigCount = 0;  // read again only after the next tile's first barrier
+            const uint32_t kb = (nValid * (uint32_t)sizeof(KeyT) + 15u) & ~15u, vb = (nValid * 4u + 15u) & ~15u;
+            fence_proxy_async();
+            mbar_expect_tx(&s.bar, kb + vb);
+            bulk_g2s(s.keys, keysIn + (size_t)tile * kTile, kb, &s.bar);
+            bulk_g2s(s.vals, valsIn + (size_t)tile * kTile, vb, &s.bar);
         }
-        else
-        {
-            if (tid == 0)
-            {
-                const uint32_t kb = (nValid * (uint32_t)sizeof(KeyT) + 15u) & ~15u, vb = (nValid * 4u + 15u) & ~15u;
-                fence_proxy_async();
-                mbar_expect_tx(&s.bar, kb + vb);
-                bulk_g2s(s.keys, keysIn + (size_t)tile * kTile, kb, &s.bar);
-                bulk_g2s(s.vals, valsIn + (size_t)tile * kTile, vb, &s.bar);
-            }
-            mbar_wait(&s.bar, parity);
-            parity ^= 1;
-        }
+        mbar_wait(&s.bar, parity);
+        parity ^= 1;
         TLREC(1);
 
         // ---- rank: warp w owns items [w*KPT*32, (w+1)*KPT*32), item j of a lane = base + j*32 + lane (memory order)
@@ -626,17 +562,12 @@ static cudaError_t launch_passes_t(KeyT* keysA, uint32_t* valsA, KeyT* keysB, ui
         std::lock_guard<std::mutex> lock(attrMutex);
         if (!attrSet[dev & 63])
         {
-            cudaError_t e = cudaFuncSetAttribute(k_sort_onesweep<KPT, KeyT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem));
+            cudaError_t e = cudaFuncSetAttribute(k_sort_onesweep<KPT, KeyT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem));
             if (e != cudaSuccess) return e;
-            if (sizeof(KeyT) == 4)
-            {
-                e = cudaFuncSetAttribute(k_sort_onesweep<KPT, KeyT, sizeof(KeyT) == 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem));
-                if (e != cudaSuccess) return e;
-            }
             attrSet[dev & 63] = true;
         }
     }
-    const int passes = ws.numCustomPasses > 0 ? ws.numCustomPasses : (endBit - beginBit + kRadixBits - 1) / kRadixBits;
+    const int passes = (endBit - beginBit + kRadixBits - 1) / kRadixBits;
     const uint64_t maxTiles = (capacity + kSortMinTileKeys - 1) / kSortMinTileKeys + 1;
     const uint32_t capTiles = (uint32_t)((capacity + Smem::kTile - 1) / Smem::kTile);
     const uint32_t ctasPerSM = KPT == 16 ? (sizeof(KeyT) == 4 ? 4u : 3u) : 5u;
@@ -657,31 +588,20 @@ static cudaError_t launch_passes_t(KeyT* keysA, uint32_t* valsA, KeyT* keysB, ui
         const uint32_t* vin = (p & 1) ? valsB : valsA;
         KeyT* kout = (p & 1) ? keysA : keysB;
         uint32_t* vout = (p & 1) ? valsA : valsB;
-        const bool custom = ws.numCustomPasses > 0;
-        const int shift = custom ? ws.customShift[p] : beginBit + p * kRadixBits;
-        const int passEnd = custom ? shift + ws.customBits[p] : endBit;
+        const int shift = beginBit + p * kRadixBits;
         const bool last = p == passes - 1;
         const bool wantNext = !last && !ws.allHistogramsReady;
-        const int nshift = last ? 0 : (custom ? ws.customShift[p + 1] : shift + kRadixBits);
-        const int nextEnd = last ? 0 : (custom ? nshift + ws.customBits[p + 1] : endBit);
+        const int nshift = last ? 0 : shift + kRadixBits;
         // a histogram row written by the kernel right before this pass: the producer's for pass 0, the previous pass's when the
         // passes accumulate each other's histograms
         const int histFromPredecessor = (p == 0 || !ws.allHistogramsReady) ? 1 : 0;
-        // the pass that creates its input (ExpandSource): u32 keys only
-        auto kernel = k_sort_onesweep<KPT, KeyT, false>;
-        if (p == 0 && ws.expand.off != nullptr)
-        {
-            if (sizeof(KeyT) != 4) return cudaErrorInvalidValue;
-            kernel = k_sort_onesweep<KPT, KeyT, sizeof(KeyT) == 4>;
-        }
         cudaError_t le = launch_kernel(
-            kernel, dim3(grid), dim3(kSortThreads), sizeof(Smem), stream, ws.pdl,
-            kin, vin, kout, vout, nDevice, shift, digit_mask(shift, passEnd), nshift, last ? 0u : digit_mask(nshift, nextEnd),
+            k_sort_onesweep<KPT, KeyT>, dim3(grid), dim3(kSortThreads), sizeof(Smem), stream, ws.pdl,
+            kin, vin, kout, vout, nDevice, shift, digit_mask(shift, endBit), nshift, last ? 0u : digit_mask(nshift, endBit),
             (const uint32_t*)(ws.histograms + (ws.passOffset + p) * kRadixSize), wantNext ? ws.histograms + (ws.passOffset + p + 1) * kRadixSize : (uint32_t*)nullptr,
             ws.status + (size_t)(ws.passOffset + p) * maxTiles * kRadixSize, ws.tickets + ws.passOffset + p, ws.generation, dTl ? dTl + p * tlWords : (unsigned long long*)nullptr,
             last && shift >= kRangeShift ? ws.tileRanges : (uint2*)nullptr, ws.numRangeTiles,  // the digit must be part of the tile id
-            (uint32_t)maxTiles, kRangeShift, ws.groupAgg ? ws.groupAgg + (size_t)p * ws.groupWordsPerPass : (unsigned long long*)nullptr, histFromPredecessor,
-            p == 0 ? ws.expand : ExpandSource{});
+            (uint32_t)maxTiles, kRangeShift, ws.groupAgg ? ws.groupAgg + (size_t)p * ws.groupWordsPerPass : (unsigned long long*)nullptr, histFromPredecessor);
         if (le != cudaSuccess) return le;
     }
 #ifdef SPL_SORT_TIMELINE
@@ -737,7 +657,7 @@ cudaError_t launch_sort_passes(unsigned long long* keysA, uint32_t* valsA, unsig
 cudaError_t launch_sort_passes32(uint32_t* keysA, uint32_t* valsA, uint32_t* keysB, uint32_t* valsB, const uint32_t* nDevice, uint64_t capacity,
                                  int beginBit, int endBit, const SortWorkspace& ws, int numSMs, cudaStream_t stream)
 {
-    const int passes = ws.numCustomPasses > 0 ? ws.numCustomPasses : (endBit - beginBit + kRadixBits - 1) / kRadixBits;
+    const int passes = (endBit - beginBit + kRadixBits - 1) / kRadixBits;
     if (passes < 1 || passes > 4 || endBit > 32) return cudaErrorInvalidValue;
     if (ws.keysPerThread == 8) return launch_passes_t<8, uint32_t>(keysA, valsA, keysB, valsB, nDevice, capacity, beginBit, endBit, ws, numSMs, stream);
     return launch_passes_t<16, uint32_t>(keysA, valsA, keysB, valsB, nDevice, capacity, beginBit, endBit, ws, numSMs, stream);

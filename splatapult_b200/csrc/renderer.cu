@@ -103,7 +103,6 @@ struct RendererImpl
     }
     int depthKpt() const { return kptFor(n); }
     int instKpt() const { return sortKptOption ? sortKptOption : 16; }  // the instance count is only known on the device
-    uint32_t* dTileStart = nullptr;  // default path: per sort tile of the first instance pass, the entry holding its first instance
     uint2* dRanges = nullptr;
     uint32_t* dTileCtl = nullptr;  // tileCount | tileCursor | largeList, rangesTiles words each
     uint4* dSide = nullptr;        // per-gaussian {rect, depthKey, count} of the binned sort
@@ -164,8 +163,8 @@ struct RendererImpl
 
     void freeFrameBuffers()
     {
-        cudaFree(dKeysA); cudaFree(dKeysB); cudaFree(dValsA); cudaFree(dValsB); cudaFree(dStatus); cudaFree(dTileStart);
-        dKeysA = dKeysB = nullptr; dValsA = dValsB = nullptr; dStatus = nullptr; dTileStart = nullptr;
+        cudaFree(dKeysA); cudaFree(dKeysB); cudaFree(dValsA); cudaFree(dValsB); cudaFree(dStatus);
+        dKeysA = dKeysB = nullptr; dValsA = dValsB = nullptr; dStatus = nullptr;
         capacity = 0;
     }
     void release()
@@ -268,7 +267,6 @@ struct RendererImpl
         CU_TRY(cudaMalloc(&dValsA, padded * 4));
         CU_TRY(cudaMalloc(&dValsB, padded * 4));
         CU_TRY(cudaMalloc(&dStatus, sort_status_bytes(want, kMaxSortPasses)));
-        CU_TRY(cudaMalloc(&dTileStart, ((want + kSortMinTileKeys - 1) / kSortMinTileKeys + 2) * sizeof(uint32_t)));
         CU_TRY(cudaMemsetAsync(dStatus, 0, sort_status_bytes(want, kMaxSortPasses), stream));
         sortGeneration = 0;
         // the padding is read (never used) by the last tile's bulk copy: keep it defined
@@ -417,47 +415,32 @@ struct RendererImpl
         return !std::memcmp(a, cam, 64) && !std::memcmp(a + 16, proj, 64) && !std::memcmp(a + 32, vp, 16) && !std::memcmp(a + 36, nf, 8);
     }
 
-    // default path, second half: scan the depth-ordered gaussian list (offsets of the tile instances each entry expands to) and
-    // sort the instances by tile -- the FIRST pass creates them in its shared-memory tiles, nobody writes them unsorted; stable
-    // passes keep the depth order; the last pass writes the tile ranges.  Instance key = (tile row << tileBitsX) | tile column,
-    // one coordinate digit per pass.  `order` is dValsA right after the depth passes, or dOrder when a shared-sort Render
-    // re-projects for another eye.
-    int tilePassesSplit() const { return tile_x_passes(fc.tileBitsX) + tile_y_passes(fc.tileBitsY); }
-    int expandAndSortTiles(const uint32_t* order, uint32_t keySpace)
+    // default path, second half: expand the depth-ordered gaussian ids into (tile id, id) instances and sort them by
+    // tile (stable passes keep the depth order); the last pass writes the tile ranges.  `order` is dValsA right after the
+    // depth passes, or dOrder when a shared-sort Render re-projects for another eye.
+    int expandAndSortTiles(const uint32_t* order, uint32_t numTiles)
     {
-        const int nXp = tile_x_passes(fc.tileBitsX), nYp = tile_y_passes(fc.tileBitsY), tilePasses = nXp + nYp;
+        const int tileBits = sortBits - kDepthBits, tilePasses = (tileBits + kRadixBits - 1) / kRadixBits;
         uint32_t* keysA32 = reinterpret_cast<uint32_t*>(dKeysA);
         uint32_t* keysB32 = reinterpret_cast<uint32_t*>(dKeysB);
-        // the scan's output lives where the depth keys were: offsets in keysA32[0, n), rectangles in the upper half of the
-        // u64-sized buffer (the u32 passes use the lower half only)
-        uint32_t* expOff = keysA32;
-        uint32_t* expRect = keysA32 + capacity;
-        const uint32_t tileKeys = (uint32_t)kSortThreads * (uint32_t)instKpt();
-        CU_TRY(launch_expand_scan(order, reinterpret_cast<const uint2*>(dSide), n, expOff, expRect, dTileStart, tileKeys, dCtr, dScan, (uint32_t)capacity, stream,
-                                  usePdl(1)));
+        CU_TRY(launch_emit_sorted(order, reinterpret_cast<const uint2*>(dSide), n, fc, keysB32, dValsB, dCtr, dScan, (uint32_t)capacity,
+                                  dHist + 4 * kRadixSize, stream, usePdl(1)));
         launches += n ? 1 : 0;
         if (profile) CU_TRY(cudaEventRecord(ev[6], stream));
+        dSortedKeys = dKeysB;
+        dSortedVals = dValsB;
         sortedKeyBytes = 4;
-        SortWorkspace wsTile{dHist, dStatus, dCtr->sortTickets, capacity, sortGeneration, instKpt(), 4, dRanges, keySpace};
-        wsTile.allHistogramsReady = true;  // k_project_keys left the histogram of every tile digit
-        wsTile.pdl = usePdl(2);
-        wsTile.groupAgg = dGroups + 4 * sort_group_words(std::max<uint32_t>(n, 1), depthKpt());
-        wsTile.groupWordsPerPass = sort_group_words(std::max<uint64_t>(capacity, 1), instKpt());
-        wsTile.numCustomPasses = tilePasses;
-        int p = 0;
-        for (int a = 0; a < nXp; a++, p++) { wsTile.customShift[p] = a * kRadixBits; wsTile.customBits[p] = std::max(1, std::min(kRadixBits, fc.tileBitsX - a * kRadixBits)); }
-        for (int b2 = 0; b2 < nYp; b2++, p++) { wsTile.customShift[p] = fc.tileBitsX + b2 * kRadixBits; wsTile.customBits[p] = std::min(kRadixBits, fc.tileBitsY - b2 * kRadixBits); }
-        wsTile.expand.off = expOff;
-        wsTile.expand.rect = expRect;
-        wsTile.expand.ids = order;
-        wsTile.expand.tileStart = dTileStart;
-        wsTile.expand.lastEntry = &dCtr->lastExpandEntry;
-        wsTile.expand.tileBitsX = fc.tileBitsX;
-        // pass 0 creates the instances into the B buffers, pass 1 sorts B -> A, ...
-        CU_TRY(launch_sort_passes32(keysA32, dValsA, keysB32, dValsB, &dCtr->usedInstances, capacity, 0, fc.tileBitsX + fc.tileBitsY, wsTile, numSMs, stream));
-        launches += tilePasses;
-        dSortedKeys = (tilePasses & 1) ? dKeysB : dKeysA;
-        dSortedVals = (tilePasses & 1) ? dValsB : dValsA;
+        if (tilePasses > 0)
+        {
+            SortWorkspace wsTile{dHist, dStatus, dCtr->sortTickets, capacity, sortGeneration, instKpt(), 4, rangesFused ? dRanges : nullptr, numTiles};
+            wsTile.allHistogramsReady = tilePasses <= 2;  // k_emit_sorted left the histograms of both tile digits
+            wsTile.pdl = usePdl(2);
+            wsTile.groupAgg = dGroups + 4 * sort_group_words(std::max<uint32_t>(n, 1), depthKpt());
+            wsTile.groupWordsPerPass = sort_group_words(std::max<uint64_t>(capacity, 1), instKpt());
+            CU_TRY(launch_sort_passes32(keysB32, dValsB, keysA32, dValsA, &dCtr->usedInstances, capacity, 0, tileBits, wsTile, numSMs, stream));
+            launches += tilePasses;
+            if (tilePasses & 1) { dSortedKeys = dKeysA; dSortedVals = dValsA; }
+        }
         return 0;
     }
 
@@ -486,8 +469,9 @@ struct RendererImpl
         rangesFused = false;
         if (profile) CU_TRY(cudaEventRecord(ev[0], stream));
         {
+            const int tilePassesNow = (sortBits - kDepthBits + kRadixBits - 1) / kRadixBits;
             const size_t clearBytes = frameSortMode == SPL_SORT_BINNED ? controlBytes
-                                      : frameSortMode == SPL_SORT_LSD_FLAT ? frameControlBytes(4, sortPasses) : frameControlBytes(4, tilePassesSplit());
+                                      : frameSortMode == SPL_SORT_LSD_FLAT ? frameControlBytes(4, sortPasses) : frameControlBytes(4, tilePassesNow);
             CU_TRY(cudaMemsetAsync(dControl, 0, clearBytes, stream));
         }
         if (frameSortMode == SPL_SORT_BINNED)
@@ -521,7 +505,7 @@ struct RendererImpl
                 ++sortGeneration;
             }
             // with more than one tile the last pass sorts on a tile-id digit and writes the tile ranges itself
-            rangesFused = numTiles > 1 || frameSortMode == SPL_SORT_LSD;  // the default path always has an instance pass
+            rangesFused = numTiles > 1;
             if (frameSortMode == SPL_SORT_LSD_FLAT)
             {
                 // every digit pass runs on the D tile instances (emitted in gaussian order by the projection kernel,
@@ -553,7 +537,7 @@ struct RendererImpl
                 uint32_t* keysA32 = reinterpret_cast<uint32_t*>(dKeysA);
                 uint32_t* keysB32 = reinterpret_cast<uint32_t*>(dKeysB);
                 nvtxRangePushA("pre-sort");  // the reference's zone names (src/splatrenderer.cpp:172,208)
-                const cudaError_t pe = launch_project_keys(cloud, fc, dRec, keysA32, dValsA, reinterpret_cast<uint2*>(dSide), dCtr, dHist, dHist + 4 * kRadixSize, stream);
+                const cudaError_t pe = launch_project_keys(cloud, fc, dRec, keysA32, dValsA, reinterpret_cast<uint2*>(dSide), dCtr, dHist, stream);
                 nvtxRangePop();
                 CU_TRY(pe);
                 launches += n ? 1 : 0;
@@ -572,7 +556,7 @@ struct RendererImpl
                     // the tile passes reuse dValsA: keep the depth order for the other eye's Render
                     CU_TRY(cudaMemcpyAsync(dOrder, dValsA, (size_t)n * sizeof(uint32_t), cudaMemcpyDeviceToDevice, stream));
                 }
-                if (int rc = expandAndSortTiles(dValsA, 1u << (fc.tileBitsX + fc.tileBitsY))) return rc;
+                if (int rc = expandAndSortTiles(dValsA, numTiles)) return rc;
             }
             if (profile) CU_TRY(cudaEventRecord(ev[2], stream));
             if (!rangesFused)
@@ -617,24 +601,19 @@ struct RendererImpl
         std::memcpy(drawArgs, lastArgs, sizeof drawArgs);
 
         const uint32_t numTiles = (uint32_t)tilesX * tilesY;
-        fc.tileBitsX = fc.tileBitsY = 0;
-        while ((1 << fc.tileBitsX) < tilesX) fc.tileBitsX++;
-        while ((1 << fc.tileBitsY) < tilesY) fc.tileBitsY++;
-        // the default path indexes the tile ranges by the instance key (row << bitsX | column), the other paths by the tile number
-        const uint32_t keySpace = std::max<uint32_t>(numTiles, 1u << (fc.tileBitsX + fc.tileBitsY));
-        if (keySpace > rangesTiles)
+        if (numTiles > rangesTiles)
         {
             CU_TRY(cudaStreamSynchronize(stream));
             cudaFree(dTileCtl);
             dTileCtl = nullptr;
-            if (int rc = allocControl(keySpace)) return rc;
-            CU_TRY(cudaMalloc(&dTileCtl, (size_t)keySpace * 3 * sizeof(uint32_t)));
-            rangesTiles = keySpace;
+            if (int rc = allocControl(numTiles)) return rc;
+            CU_TRY(cudaMalloc(&dTileCtl, (size_t)numTiles * 3 * sizeof(uint32_t)));
+            rangesTiles = numTiles;
         }
         int tileBits = 0;
         while ((1u << tileBits) < numTiles) tileBits++;
-        sortBits = kDepthBits + (sortMode == SPL_SORT_LSD ? fc.tileBitsX + fc.tileBitsY : tileBits);
-        sortPasses = sortMode == SPL_SORT_LSD ? 4 + tilePassesSplit() : (sortBits + kRadixBits - 1) / kRadixBits;
+        sortBits = kDepthBits + tileBits;
+        sortPasses = (sortBits + kRadixBits - 1) / kRadixBits;
 
         if (profile && !evCreated)
         {
@@ -714,11 +693,11 @@ struct RendererImpl
         }
         launches = 0;
         if (profile) CU_TRY(cudaEventRecord(ev[0], stream));
-        CU_TRY(cudaMemsetAsync(dControl, 0, frameControlBytes(4, tilePassesSplit()), stream));  // counters, histograms, scan state, tile ranges, group words
-        CU_TRY(launch_project_keys(cloud, fc, dRec, nullptr, nullptr, reinterpret_cast<uint2*>(dSide), dCtr, dHist, dHist + 4 * kRadixSize, stream));
+        CU_TRY(cudaMemsetAsync(dControl, 0, frameControlBytes(4, (sortBits - kDepthBits + kRadixBits - 1) / kRadixBits), stream));  // counters, histograms, scan state, tile ranges, group words
+        CU_TRY(launch_project_keys(cloud, fc, dRec, nullptr, nullptr, reinterpret_cast<uint2*>(dSide), dCtr, dHist, stream));
         launches += n ? 1 : 0;
         if (profile) CU_TRY(cudaEventRecord(ev[1], stream));
-        if (int rc = expandAndSortTiles(dOrder, 1u << (fc.tileBitsX + fc.tileBitsY))) return rc;
+        if (int rc = expandAndSortTiles(dOrder, numTiles)) return rc;
         if (profile) CU_TRY(cudaEventRecord(ev[2], stream));
         if (!rangesFused)
         {
@@ -788,8 +767,7 @@ struct RendererImpl
         const FrameReport report{dCtr, dReport + seq % kReportRing, (seq & ((1ull << (64 - kReportSeqShift)) - 1)) << kReportSeqShift};
         nvtxRangePushA("draw");  // the reference's zone name (src/splatrenderer.cpp:323)
         const cudaError_t ce = launch_composite(dRanges, binned ? reinterpret_cast<const uint32_t*>(dKeysA) : sortedVals(), binned ? 2 : 1, dRec, dFb, fbFormat, fc.width,
-                                                fc.height, fc.tilesX, fc.tilesY, frameSortMode == SPL_SORT_LSD ? fc.tileBitsX : -1, (float)earlyOutT, subblockCull,
-                                                rangesFused ? kFusedRangeBeginXor : 0u, report, stream,
+                                                fc.height, fc.tilesX, fc.tilesY, (float)earlyOutT, subblockCull, rangesFused ? kFusedRangeBeginXor : 0u, report, stream,
                                                 usePdl(3) && frameSortMode == SPL_SORT_LSD);
         nvtxRangePop();
         CU_TRY(ce);
@@ -972,14 +950,8 @@ struct RendererImpl
             if (d) CU_TRY(cudaMemcpyAsync(ids.data(), sortedVals(), d * 4, cudaMemcpyDeviceToHost, stream));
             if (n) CU_TRY(cudaMemcpyAsync(recs.data(), dRec, (size_t)n * sizeof(ProjRecord), cudaMemcpyDeviceToHost, stream));
             CU_TRY(cudaStreamSynchronize(stream));
-            // the instances are keyed (tile row << bitsX | tile column): the tap shows tile NUMBERS (row * tilesX + column), the same
-            // order
-            const uint32_t maskX = (1u << fc.tileBitsX) - 1u;
             for (size_t k = 0; k < d; k++)
-            {
-                const unsigned long long tile = (unsigned long long)(tiles[k] >> fc.tileBitsX) * fc.tilesX + (tiles[k] & maskX);
-                static_cast<unsigned long long*>(host)[k] = (tile << 32) | (ids[k] < n ? recs[ids[k]].key : 0u);
-            }
+                static_cast<unsigned long long*>(host)[k] = ((unsigned long long)tiles[k] << 32) | (ids[k] < n ? recs[ids[k]].key : 0u);
             return ok();
         }
         switch (what)
@@ -991,24 +963,6 @@ struct RendererImpl
         default: return fail(SPL_ERR_ARG, "unknown tap");
         }
         if (bytes < have) return fail(SPL_ERR_ARG, "tap buffer too small");
-        if (what == SPL_TAP_TILE_RANGES && frameSortMode == SPL_SORT_LSD)
-        {
-            // default path: the ranges are indexed by the instance key; the tap is indexed by tile number
-            const size_t keySpace = (size_t)1 << (fc.tileBitsX + fc.tileBitsY);
-            std::vector<uint2> keyed(keySpace);
-            CU_TRY(cudaMemcpyAsync(keyed.data(), dRanges, keySpace * sizeof(uint2), cudaMemcpyDeviceToHost, stream));
-            CU_TRY(cudaStreamSynchronize(stream));
-            uint2* r = static_cast<uint2*>(host);
-            for (int ty = 0; ty < fc.tilesY; ty++)
-                for (int tx = 0; tx < fc.tilesX; tx++)
-                {
-                    uint2 v = keyed[((size_t)ty << fc.tileBitsX) | (size_t)tx];
-                    if (v.y == 0) v.x = 0;  // a tile the sort never touched reads {0, 0}
-                    else v.x ^= kFusedRangeBeginXor;
-                    r[(size_t)ty * fc.tilesX + tx] = v;
-                }
-            return ok();
-        }
         if (have) CU_TRY(cudaMemcpyAsync(host, src, have, cudaMemcpyDeviceToHost, stream));
         CU_TRY(cudaStreamSynchronize(stream));
         if (what == SPL_TAP_TILE_RANGES && rangesFused)
