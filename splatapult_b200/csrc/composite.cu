@@ -21,7 +21,7 @@
 //   * while staging, each entry gets an 8-bit mask of the 8x8 blocks its discard ellipse reaches (exact); a warp
 //     ballots the masks of 32 entries at a time and evaluates only its hits -- warp-uniform, no divergence;
 //   * the two pixels of a thread are evaluated with Blackwell's packed FP32 pipe (fma.rn.f32x2 -> SASS FFMA2, whose
-//     operands may each be a scalar broadcast): log2 w = c0 + u (c1 + hA u + hB v) + v (c2 + hC v) is 5 FFMA2 for both
+//     operands may each be a scalar broadcast): log2 w = [c0 + u (c1 + hA u)] + v (c2 + hB u + hC v) is 2 FFMA + 3 FFMA2 for both
 //     pixels (they share u), the weight and the three colour accumulators 1 FMUL2 + 3 FFMA2 + 1 FADD2 -- a 24-instruction
 //     hit body per 64 pixels where one pixel per thread took 21 per 32; the walk (FLO, BMSK, LOP3, LEA, 3 LDS, BRA) is
 //     paid once per pair.  8x8 blocks are hit by 0.61x as many (entry, block) pairs as 8x4 ones (benchmarks/hit_model.py).
@@ -181,7 +181,7 @@ k_composite(const uint2* ranges, const uint32_t* vals, int idStride, const ProjR
         {
         // log2 w as a polynomial in the pixel's offset (u, v) from the TILE centre: with d0 = tile centre - splat centre,
         //   log2 w = hA (dx0+u)^2 + hB (dx0+u)(dy0+v) + hC (dy0+v)^2 + L = c0 + c1 u + c2 v + hA u^2 + hB uv + hC v^2
-        // evaluated per pixel pair as c0 + u (c1 + hA u + hB v) + v (c2 + hC v): 5 FFMA2; the rounding error is that of the
+        // evaluated per pixel pair as [c0 + u (c1 + hA u)] + v (c2 + hB u + hC v): 2 FFMA + 3 FFMA2; the rounding error is that of the
         // direct form (same term magnitudes).
         const float kLog2e = 1.4426950408889634f;
         const float h = -0.5f * kLog2e;
@@ -294,39 +294,10 @@ k_composite(const uint2* ranges, const uint32_t* vals, int idStride, const ProjR
             {
                 uint32_t hits;  // slots past the list's end hold 0
                 asm volatile("ld.shared.u32 %0, [%1];" : "=r"(hits) : "r"(hitAddr));
-                // one list entry against this thread's two pixels
-                auto load_entry = [&](uint32_t addr, float4& a, float4& b, float& blue) {
-                    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w) : "r"(addr));
-                    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4+%5];"
-                                 : "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w)
-                                 : "r"(addr), "n"(sizeof(CompSmem::a)));
-                    asm volatile("ld.shared.f32 %0, [%1+%2];" : "=f"(blue) : "r"(addr), "n"(sizeof(CompSmem::a) + sizeof(CompSmem::b)));
-                };
-                auto weight = [&](const float4& a, const float4& b) -> f32x2 {
-                    // log2 w = c0 + u (c1 + hA u + hB v) + v (c2 + hC v)
-                    f32x2 t1 = fma2(bcast2(b.x), pv, bcast2(a.y));
-                    t1 = fma2(bcast2(a.w), pu2, t1);
-                    const f32x2 t2 = fma2(bcast2(b.y), pv, bcast2(a.z));
-                    f32x2 pw = fma2(pu2, t1, bcast2(a.x));
-                    pw = fma2(pv, t2, pw);
-                    float pw0, pw1;
-                    unpack2(pw, pw0, pw1);
-                    float w0 = ex2_approx(pw0), w1 = ex2_approx(pw1);
-                    w0 = (w0 > kDiscard) ? w0 : 0.0f;  // discard iff w <= 1/256 (splat_frag.glsl:38)
-                    w1 = (w1 > kDiscard) ? w1 : 0.0f;
-                    return pack2(w0, w1);
-                };
-                auto blend = [&](f32x2 w, const float4& b, float blue) {
-                    const f32x2 tw = mul2(T, w);
-                    cr = fma2(bcast2(b.z), tw, cr);
-                    cg = fma2(bcast2(b.w), tw, cg);
-                    cb = fma2(bcast2(blue), tw, cb);
-                    T = sub2(T, tw);
-                };
                 while (hits)
                 {
-                    // hit body, two pixels per thread: FLO, BMSK, LOP3, LEA for the walk; 3 LDS; 5 FFMA2 (log2 w of both pixels),
-                    // 2 MUFU.EX2, 2 FSETP + 2 FSEL (discard), FMUL2, 3 FFMA2, FADD2; BRA
+                    // hit body, two pixels per thread: FLO, BMSK, LOP3, LEA for the walk; 3 LDS; 2 FFMA + 3 FFMA2 (log2 w of both
+                    // pixels), 2 MUFU.EX2, 2 FSETP + 2 FSEL (discard), FMUL2, 3 FFMA2, FADD2; BRA
                     uint32_t top, below;
                     asm("bfind.u32 %0, %1;" : "=r"(top) : "r"(hits));                       // index of the highest set bit
                     asm("bmsk.clamp.b32 %0, %1, %2;" : "=r"(below) : "r"(0), "r"(top));   // bits [0, top)
@@ -339,12 +310,14 @@ k_composite(const uint2* ranges, const uint32_t* vals, int idStride, const ProjR
                                  : "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w)
                                  : "r"(addr), "n"(sizeof(CompSmem::a)));
                     asm volatile("ld.shared.f32 %0, [%1+%2];" : "=f"(blue) : "r"(addr), "n"(sizeof(CompSmem::a) + sizeof(CompSmem::b)));
-                    // log2 w = c0 + u (c1 + hA u + hB v) + v (c2 + hC v)
-                    f32x2 t1 = fma2(bcast2(b.x), pv, bcast2(a.y));
-                    t1 = fma2(bcast2(a.w), pu2, t1);
-                    const f32x2 t2 = fma2(bcast2(b.y), pv, bcast2(a.z));
-                    f32x2 pw = fma2(pu2, t1, bcast2(a.x));
-                    pw = fma2(pv, t2, pw);
+                    // log2 w = [c0 + u (c1 + hA u)] + v (c2 + hB u + hC v): the bracket is the same for both pixels (they share u) --
+                    // two scalar FFMA --, the rest three FFMA2; the dependent chain is three deep (t2 -> t2 -> pw), the bracket runs
+                    // beside it
+                    const float s1 = fmaf(a.w, pu, a.y);
+                    const float s0 = fmaf(pu, s1, a.x);
+                    f32x2 t2 = fma2(bcast2(b.y), pv, bcast2(a.z));
+                    t2 = fma2(bcast2(b.x), pu2, t2);
+                    const f32x2 pw = fma2(pv, t2, bcast2(s0));
                     float pw0, pw1;
                     unpack2(pw, pw0, pw1);
                     float w0 = ex2_approx(pw0), w1 = ex2_approx(pw1);
