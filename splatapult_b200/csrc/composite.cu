@@ -294,15 +294,18 @@ k_composite(const uint2* ranges, const uint32_t* vals, int idStride, const ProjR
             {
                 uint32_t hits;  // slots past the list's end hold 0
                 asm volatile("ld.shared.u32 %0, [%1];" : "=r"(hits) : "r"(hitAddr));
+                // the index of the NEXT hit is found (FLO runs on the slow XU pipe) while the current one is evaluated
+                uint32_t top;
+                asm("bfind.u32 %0, %1;" : "=r"(top) : "r"(hits));  // index of the highest set bit (0xffffffff for 0: unused then)
                 while (hits)
                 {
-                    // hit body, two pixels per thread: FLO, BMSK, LOP3, LEA for the walk; 3 LDS; 2 FFMA + 3 FFMA2 (log2 w of both
+                    // hit body, two pixels per thread: BMSK, LOP3, LEA, FLO for the walk; 3 LDS; 2 FFMA + 3 FFMA2 (log2 w of both
                     // pixels), 2 MUFU.EX2, 2 FSETP + 2 FSEL (discard), FMUL2, 3 FFMA2, FADD2; BRA
-                    uint32_t top, below;
-                    asm("bfind.u32 %0, %1;" : "=r"(top) : "r"(hits));                       // index of the highest set bit
+                    uint32_t below;
                     asm("bmsk.clamp.b32 %0, %1, %2;" : "=r"(below) : "r"(0), "r"(top));   // bits [0, top)
                     hits &= below;
                     const uint32_t addr = groupAddr + top * 16u;
+                    asm("bfind.u32 %0, %1;" : "=r"(top) : "r"(hits));
                     float4 a, b;
                     float blue;
                     asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w) : "r"(addr));
