@@ -216,7 +216,10 @@ SPL_API int spl_cameras_estimate_floor_plane(const spl_cameras*, float normal_ou
 SPL_API spl_sorter* spl_sorter_create(int device, uint64_t capacity);
 SPL_API void spl_sorter_destroy(spl_sorter*);
 /* stable ascending LSD sort of n (u64 key, u32 val) pairs on bits [begin_bit, end_bit); device pointers;
- * result lands in (keys_out, vals_out) which must not alias the inputs (inputs are clobbered). */
+ * result lands in (keys_out, vals_out) which must not alias the inputs (inputs are clobbered).
+ * All four pointers must be 16-byte aligned (SPL_ERR_ARG otherwise) and every buffer must extend at least 16 bytes past
+ * its n-th element: tiles are staged by the TMA engine (cp.async.bulk), which moves whole 16-byte units, so the last tile
+ * reads up to 12 bytes past the last value / 8 past the last key (never used). */
 SPL_API int spl_sorter_sort(spl_sorter*, void* d_keys_in, void* d_vals_in, void* d_keys_out, void* d_vals_out,
                             uint64_t n, int begin_bit, int end_bit, void* cuda_stream);
 /* convenience for tests: host arrays in, host arrays out */

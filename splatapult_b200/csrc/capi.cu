@@ -377,6 +377,9 @@ int spl_sorter_sort(spl_sorter* s, void* d_keys_in, void* d_vals_in, void* d_key
     if (!s || !d_keys_in || !d_vals_in || !d_keys_out || !d_vals_out) return set_error(SPL_ERR_ARG, "null argument");
     if (n > s->capacity || n > splat::kMaxInstances) return set_error(SPL_ERR_ARG, "n exceeds sorter capacity");
     if (begin_bit < 0 || end_bit > 64 || end_bit <= begin_bit) return set_error(SPL_ERR_ARG, "bad bit range");
+    if ((reinterpret_cast<uintptr_t>(d_keys_in) | reinterpret_cast<uintptr_t>(d_vals_in) | reinterpret_cast<uintptr_t>(d_keys_out) |
+         reinterpret_cast<uintptr_t>(d_vals_out)) & 15u)
+        return set_error(SPL_ERR_ARG, "sort buffers must be 16-byte aligned (tiles are staged by cp.async.bulk)");
     SORTER_TRY(cudaSetDevice(s->device));
     cudaStream_t stream = static_cast<cudaStream_t>(cuda_stream);
     const int passes = (end_bit - begin_bit + splat::kRadixBits - 1) / splat::kRadixBits;
