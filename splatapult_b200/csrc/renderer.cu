@@ -59,6 +59,7 @@ struct RendererImpl
     bool graphOption = true;           // SPL_OPT_GRAPH: replay a Sort's device work as one CUDA graph
     cudaGraphExec_t sortExec = nullptr;
     uint64_t warmFrames = 0;           // frames enqueued directly since the last configuration change
+    uint64_t sortExecShape = 0;        // graphShape() the executable graph was instantiated for
     // SPL_OPT_PDL: which kernels of a frame are launched as programmatic dependents of the kernel before them
     // (bit 0: depth passes, bit 1: emission, bit 2: tile passes, bit 3: compositor); stage events between the kernels
     // (profile mode) would break the chain
@@ -102,6 +103,16 @@ struct RendererImpl
         return (keys + kSortTileKeys - 1) / kSortTileKeys < (uint64_t)numSMs * 4 ? 8 : 16;
     }
     int depthKpt() const { return kptFor(n); }
+    // what decides WHICH nodes a captured Sort consists of (kernel variants, pass counts): cudaGraphExecUpdate only takes
+    // parameter changes, so an executable graph of another shape is dropped, not updated
+    uint64_t graphShape() const
+    {
+        uint64_t h = 1469598103934665603ull;
+        auto mix = [&](uint64_t v) { h = (h ^ v) * 1099511628211ull; };
+        mix(sortMode); mix(fc.stereoPass); mix(sortPasses); mix(sortBits); mix(pdlMask); mix(sortKptOption); mix(depthKpt());
+        mix(n); mix(cloud.shMode); mix(rangesTiles);
+        return h;
+    }
     int instKpt() const { return sortKptOption ? sortKptOption : 16; }  // the instance count is only known on the device
     uint2* dRanges = nullptr;
     uint32_t* dTileCtl = nullptr;  // tileCount | tileCursor | largeList, rangesTiles words each
@@ -642,13 +653,20 @@ struct RendererImpl
             if (rc) { if (g) cudaGraphDestroy(g); return rc; }
             if (ce != cudaSuccess) return fail(SPL_ERR_CUDA, std::string("cudaStreamEndCapture: ") + cudaGetErrorString(ce));
             bool haveExec = false;
+            const uint64_t shape = graphShape();
+            if (sortExec && sortExecShape != shape)
+            {
+                cudaGraphExecDestroy(sortExec);
+                sortExec = nullptr;
+            }
+            sortExecShape = shape;
             if (sortExec)
             {
                 cudaGraphExecUpdateResultInfo info{};
                 haveExec = cudaGraphExecUpdate(sortExec, g, &info) == cudaSuccess;
                 if (!haveExec)
                 {
-                    cudaGetLastError();  // topology changed (other pass count / kernel variant): instantiate again
+                    cudaGetLastError();  // a shape change graphShape() does not know of: instantiate again
                     cudaGraphExecDestroy(sortExec);
                     sortExec = nullptr;
                 }
@@ -1111,16 +1129,19 @@ bool SplatRenderer::SetOption(int option, double value)
     case SPL_OPT_SORT_TILE:
         if (value != 0 && value != 2048 && value != 4096) { status = SPL_ERR_ARG; error = "sort tile must be 0 (automatic), 2048 or 4096 keys"; return false; }
         impl->sortKptOption = value == 0 ? 0 : (value == 2048 ? 8 : 16);
+        impl->warmFrames = 0;  // other kernel variants: their one-time CUDA calls must not land inside a capture
         break;
     case SPL_OPT_SORT_MODE:
         if (value != SPL_SORT_BINNED && value != SPL_SORT_LSD && value != SPL_SORT_LSD_FLAT) { status = SPL_ERR_ARG; error = "unknown sort mode"; return false; }
         impl->sortMode = (int)value;
         impl->haveSort = false;
+        impl->warmFrames = 0;
         break;
     case SPL_OPT_SHARED_SORT:
         if (value != 0 && value != 1) { status = SPL_ERR_ARG; error = "shared sort must be 0 or 1"; return false; }
         impl->sharedSort = value != 0;
         impl->haveSort = false;
+        impl->warmFrames = 0;
         break;
     case SPL_OPT_GRAPH:
         if (value != 0 && value != 1) { status = SPL_ERR_ARG; error = "graph must be 0 or 1"; return false; }
@@ -1130,6 +1151,7 @@ bool SplatRenderer::SetOption(int option, double value)
     case SPL_OPT_PDL:
         if (value < 0 || value > 15 || value != (int)value) { status = SPL_ERR_ARG; error = "pdl must be a mask 0..15"; return false; }
         impl->pdlMask = (int)value;
+        impl->warmFrames = 0;
         break;
     case SPL_OPT_SUBBLOCK_CULL:
         if (value != 0 && value != 1 && value != 2) { status = SPL_ERR_ARG; error = "sub-block cull mode must be 0, 1 or 2"; return false; }
