@@ -79,3 +79,36 @@ def test_pdl_with_async_readback_and_other_paths(splat, scratch):
         else:
             for a, b in zip(ref, frames):
                 np.testing.assert_array_equal(a, b)
+
+
+def test_graph_follows_configuration_changes(splat, scratch):
+    """one renderer, graph on, the frame's SHAPE changing under it: viewport sizes with other tile-bit counts (other pass
+    counts), sort modes, sort tile sizes, shared sort.  Every frame equals a fresh stream-order renderer's frame: an
+    executable graph of another node sequence is dropped and instantiated again, never replayed."""
+    ply = scenes.write_synthetic_ply(os.path.join(str(scratch), "modes_shape.ply"), 25000, 0, seed=23)
+    cam = scenes.translate(0, 0, 8.0)
+    steps = [((320, 200), api.SORT_LSD, 0, 0), ((320, 200), api.SORT_LSD, 0, 0), ((1280, 720), api.SORT_LSD, 0, 0), ((64, 48), api.SORT_LSD, 0, 0),
+             ((640, 360), api.SORT_LSD_FLAT, 0, 0), ((640, 360), api.SORT_BINNED, 0, 0), ((640, 360), api.SORT_LSD, 2048, 0),
+             ((640, 360), api.SORT_LSD, 4096, 1), ((640, 360), api.SORT_LSD, 0, 0), ((1920, 1080), api.SORT_LSD, 0, 0)]
+    live = splat.SplatRenderer()
+    live.InitFromPly(ply, True, False)
+    live.SetOption(api.OPT_GRAPH, 1)
+    for (w, h), mode, tile, shared in steps:
+        proj = scenes.perspective(scenes.FOVY, w / h)
+        fresh = splat.SplatRenderer()
+        fresh.InitFromPly(ply, True, False)
+        fresh.SetOption(api.OPT_GRAPH, 0)
+        fresh.SetOption(api.OPT_PDL, 0)
+        for r in (live, fresh):
+            r.SetOption(api.OPT_SORT_MODE, mode)
+            r.SetOption(api.OPT_SORT_TILE, tile)
+            r.SetOption(api.OPT_SHARED_SORT, shared)
+        got = None
+        for _ in range(3):  # direct frame, first capture, update
+            live.Sort(cam, proj, [0, 0, w, h], NF)
+            live.Render(cam, proj, [0, 0, w, h], NF)
+            got = live.ReadFramebuffer()
+        fresh.Sort(cam, proj, [0, 0, w, h], NF)
+        fresh.Render(cam, proj, [0, 0, w, h], NF)
+        np.testing.assert_array_equal(got, fresh.ReadFramebuffer(), err_msg=str(((w, h), mode, tile, shared)))
+        fresh.close()
