@@ -46,6 +46,30 @@ REF_API int ref_import_ply(const char* path, int importFullSH, size_t* n, size_t
     return 0;
 }
 
+// GaussianCloud::PruneSplats (src/gaussiancloud.cpp:581-626) on an imported file: the kept records, in the reference's order
+REF_API int ref_prune_splats(const char* path, int importFullSH, const float* origin, uint32_t keep, size_t* n, size_t* stride, float* out, size_t capFloats)
+{
+    GaussianCloud::Options opt{importFullSH != 0, true};
+    GaussianCloud gc(opt);
+    if (!gc.ImportPly(path)) return -1;
+    gc.PruneSplats(glm::vec3(origin[0], origin[1], origin[2]), keep);
+    *n = gc.GetNumGaussians();
+    *stride = gc.GetStride();
+    if (!out) return 0;
+    if (capFloats * 4 < gc.GetTotalSize()) return -2;
+    std::memcpy(out, gc.GetRawDataPtr(), gc.GetTotalSize());
+    return 0;
+}
+
+// GaussianCloud::ExportPly (src/gaussiancloud.cpp:367-503) of an imported file, written by the reference's own Ply::Dump
+REF_API int ref_export_ply(const char* inPath, int importFullSH, int exportFullSH, const char* outPath)
+{
+    GaussianCloud::Options opt{importFullSH != 0, exportFullSH != 0};
+    GaussianCloud gc(opt);
+    if (!gc.ImportPly(inPath)) return -1;
+    return gc.ExportPly(outPath) ? 0 : -2;
+}
+
 REF_API int ref_init_debug_cloud(float* out, size_t capFloats)
 {
     GaussianCloud::Options opt{true, true};

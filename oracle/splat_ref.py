@@ -29,6 +29,10 @@ def lib() -> C.CDLL:
         L.ref_import_ply.restype = C.c_int
         L.ref_init_debug_cloud.argtypes = [C.c_void_p, C.c_size_t]
         L.ref_init_debug_cloud.restype = C.c_int
+        L.ref_prune_splats.argtypes = [C.c_char_p, C.c_int, C.POINTER(C.c_float), C.c_uint32, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t), C.c_void_p, C.c_size_t]
+        L.ref_prune_splats.restype = C.c_int
+        L.ref_export_ply.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_char_p]
+        L.ref_export_ply.restype = C.c_int
         fp = C.POINTER(C.c_float)
         L.ref_render.argtypes = [C.c_void_p, C.c_size_t, C.c_size_t, C.c_int, C.c_int, fp, fp, fp, fp, C.c_void_p, C.c_void_p, C.c_void_p]
         L.ref_render.restype = C.c_size_t
@@ -46,6 +50,26 @@ def import_ply(path: str, import_full_sh: bool = True):
     rc = lib().ref_import_ply(path.encode(), int(import_full_sh), C.byref(n), C.byref(stride), C.byref(full), aos.ctypes.data, aos.size)
     assert rc == 0
     return aos, bool(full.value)
+
+
+def prune_splats(path: str, origin, keep: int, import_full_sh: bool = True) -> np.ndarray:
+    """GaussianCloud::PruneSplats of the reference on an imported file: the kept records in the reference's order"""
+    o = (C.c_float * 3)(*[float(x) for x in origin])
+    n, stride = C.c_size_t(), C.c_size_t()
+    rc = lib().ref_prune_splats(path.encode(), int(import_full_sh), o, int(keep), C.byref(n), C.byref(stride), None, 0)
+    if rc:
+        raise IOError(f"reference ImportPly returned false for {path}")
+    aos = np.zeros((n.value, stride.value // 4), np.float32)
+    rc = lib().ref_prune_splats(path.encode(), int(import_full_sh), o, int(keep), C.byref(n), C.byref(stride), aos.ctypes.data, aos.size)
+    assert rc == 0
+    return aos
+
+
+def export_ply(in_path: str, out_path: str, import_full_sh: bool = True, export_full_sh: bool = False) -> None:
+    """GaussianCloud::ExportPly of the reference (its own Ply::Dump writes the file)"""
+    rc = lib().ref_export_ply(in_path.encode(), int(import_full_sh), int(export_full_sh), out_path.encode())
+    if rc:
+        raise IOError(f"reference ExportPly failed ({rc}) for {in_path} -> {out_path}")
 
 
 def debug_cloud() -> np.ndarray:
