@@ -4,8 +4,8 @@
 
 The reference's hot path cannot be built the normal way here (OpenGL 4.6 / GLEW / SDL2 / glm / Eigen are absent and
 its build is cmake + vcpkg), so this recipe compiles exactly the files that carry the path's arithmetic:
-  * host C++   src/gaussiancloud.cpp, src/ply.cpp, src/core/binaryattribute.cpp, src/core/log.cpp  -- unmodified, against
-               oracle/ref_shim/{glm/glm.hpp, Eigen/Dense} stand-ins;
+  * host C++   src/gaussiancloud.cpp, src/camerasconfig.cpp, src/ply.cpp, src/core/binaryattribute.cpp, src/core/log.cpp  --
+               unmodified, against oracle/ref_shim/{glm/glm.hpp, Eigen/Dense, nlohmann/json.hpp} stand-ins;
   * GLSL       shader/presort_compute.glsl, splat_vert.glsl (4 variants: FULL_SH x FRAMEBUFFER_SRGB), splat_geom.glsl,
                splat_frag.glsl -- their text is wrapped into C++ namespaces after the mechanical rewrites below (GLSL
                declarations C++ has no syntax for) and compiled against oracle/ref_shim/glsl_shim.h.
@@ -79,10 +79,10 @@ def build(force: bool = False) -> str | None:
     oracle/_ref/libsplat_ref.so that travelled with the snapshot is used as is)."""
     if not available():
         return LIB if os.path.exists(LIB) else None
-    srcs = [os.path.join(REF, "src", f) for f in ("gaussiancloud.cpp", "ply.cpp", os.path.join("core", "binaryattribute.cpp"), os.path.join("core", "log.cpp"))]
+    srcs = [os.path.join(REF, "src", f) for f in ("gaussiancloud.cpp", "camerasconfig.cpp", "ply.cpp", os.path.join("core", "binaryattribute.cpp"), os.path.join("core", "log.cpp"))]
     deps = srcs + [os.path.join(REF, "shader", v[0]) for v in VARIANTS] + [os.path.join(HERE, "ref_harness.cpp"), os.path.abspath(__file__),
                                                                             os.path.join(HERE, "ref_shim", "glsl_shim.h"), os.path.join(HERE, "ref_shim", "glm", "glm.hpp"),
-                                                                            os.path.join(HERE, "ref_shim", "Eigen", "Dense")]
+                                                                            os.path.join(HERE, "ref_shim", "Eigen", "Dense"), os.path.join(HERE, "ref_shim", "nlohmann", "json.hpp")]
     if not force and os.path.exists(LIB) and all(os.path.getmtime(LIB) >= os.path.getmtime(d) for d in deps):
         return LIB
     os.makedirs(OUT_DIR, exist_ok=True)

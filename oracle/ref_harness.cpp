@@ -19,6 +19,7 @@
 #include <memory>
 #include <vector>
 
+#include "camerasconfig.h"  // the reference's header (src/camerasconfig.h)
 #include "gaussiancloud.h"  // the reference's header (src/gaussiancloud.h)
 #include "glsl_shim.h"
 
@@ -44,6 +45,44 @@ REF_API int ref_import_ply(const char* path, int importFullSH, size_t* n, size_t
     if (capFloats * 4 < gc.GetTotalSize()) return -2;
     std::memcpy(out, gc.GetRawDataPtr(), gc.GetTotalSize());
     return 0;
+}
+
+// src/core/util.cpp is full of GL calls and is not compiled; CamerasConfig::EstimateFloorPlane needs this one function of
+// it, restated from src/core/util.cpp:128-139 (normalize, or the fallback for a zero vector)
+glm::vec3 SafeNormalize(const glm::vec3& v, const glm::vec3& ifZero)
+{
+    const float len = glm::length(v);
+    return len > 0.0f ? glm::normalize(v) : ifZero;
+}
+
+// CamerasConfig::ImportJson (src/camerasconfig.cpp:20-67) + EstimateFloorPlane (:69-96), executed by the reference's source.
+// mats: 16 floats per camera, column-major (glm layout); fovs: 2 per camera; floor: normal[3] then position[3]
+REF_API int ref_cameras_import(const char* path, float* mats, float* fovs, size_t capCameras, float* floor6)
+{
+    CamerasConfig cc;
+    if (!cc.ImportJson(path)) return -1;
+    const auto& v = cc.GetCameraVec();
+    if (mats && fovs)
+    {
+        if (v.size() > capCameras) return -2;
+        for (size_t i = 0; i < v.size(); i++)
+        {
+            for (int c = 0; c < 4; c++)
+            {
+                mats[i * 16 + c * 4 + 0] = v[i].mat[c].x; mats[i * 16 + c * 4 + 1] = v[i].mat[c].y;
+                mats[i * 16 + c * 4 + 2] = v[i].mat[c].z; mats[i * 16 + c * 4 + 3] = v[i].mat[c].w;
+            }
+            fovs[i * 2 + 0] = v[i].fov.x;
+            fovs[i * 2 + 1] = v[i].fov.y;
+        }
+    }
+    if (floor6)
+    {
+        glm::vec3 nrm, pos;
+        cc.EstimateFloorPlane(nrm, pos);
+        floor6[0] = nrm.x; floor6[1] = nrm.y; floor6[2] = nrm.z; floor6[3] = pos.x; floor6[4] = pos.y; floor6[5] = pos.z;
+    }
+    return (int)v.size();
 }
 
 // GaussianCloud::PruneSplats (src/gaussiancloud.cpp:581-626) on an imported file: the kept records, in the reference's order

@@ -1,5 +1,5 @@
 // Minimal stand-in for the parts of glm 1.0.1 that the reference's HOST sources on the hot path use
-// (src/gaussiancloud.cpp, src/core/util.h).  TEST INFRASTRUCTURE for oracle/_ref only.
+// (src/gaussiancloud.cpp, src/camerasconfig.cpp, src/core/util.h).  TEST INFRASTRUCTURE for oracle/_ref only.
 // Operation order follows glm's published implementations (type_mat3x3.inl, gtc/quaternion.inl, func_geometric.inl).
 #pragma once
 #include <cmath>
@@ -16,12 +16,25 @@ struct vec3
     float& operator[](int i) { return (&x)[i]; }
     float operator[](int i) const { return (&x)[i]; }
     vec3& operator*=(float s) { x *= s; y *= s; z *= s; return *this; }
+    vec3& operator+=(const vec3& o) { x += o.x; y += o.y; z += o.z; return *this; }
+    explicit vec3(const struct vec4& v);
 };
-struct vec4 { float x, y, z, w; vec4() : x(0), y(0), z(0), w(0) {} vec4(float a, float b, float c, float d) : x(a), y(b), z(c), w(d) {} };
+struct vec4
+{
+    float x, y, z, w;
+    vec4() : x(0), y(0), z(0), w(0) {}
+    vec4(float a, float b, float c, float d) : x(a), y(b), z(c), w(d) {}
+    vec4(const vec3& v, float d) : x(v.x), y(v.y), z(v.z), w(d) {}
+};
+inline vec3::vec3(const vec4& v) : x(v.x), y(v.y), z(v.z) {}
+inline vec3 operator-(const vec3& a) { return vec3(-a.x, -a.y, -a.z); }
+inline vec3 operator*(float s, const vec3& v) { return vec3(s * v.x, s * v.y, s * v.z); }
+inline vec3 operator*(const vec3& v, float s) { return vec3(v.x * s, v.y * s, v.z * s); }
 inline vec3 operator-(const vec3& a, const vec3& b) { return vec3(a.x - b.x, a.y - b.y, a.z - b.z); }
 inline float dot(const vec3& a, const vec3& b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
 inline float length(const vec3& v) { return std::sqrt(dot(v, v)); }
 inline float distance(const vec3& a, const vec3& b) { return length(b - a); }
+inline vec3 normalize(const vec3& v) { return v * (1.0f / std::sqrt(dot(v, v))); }  // func_geometric.inl: v * inversesqrt(dot(v, v))
 
 struct quat
 {
@@ -67,6 +80,10 @@ struct mat3
 struct mat4
 {
     vec4 c[4];
+    mat4() {}
+    mat4(const vec4& a, const vec4& b, const vec4& d, const vec4& e) { c[0] = a; c[1] = b; c[2] = d; c[3] = e; }
+    vec4& operator[](int i) { return c[i]; }
+    const vec4& operator[](int i) const { return c[i]; }
     float& at(int col, int row) { return (&c[col].x)[row]; }
     float at(int col, int row) const { return (&c[col].x)[row]; }
 };

@@ -33,6 +33,8 @@ def lib() -> C.CDLL:
         L.ref_prune_splats.restype = C.c_int
         L.ref_export_ply.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_char_p]
         L.ref_export_ply.restype = C.c_int
+        L.ref_cameras_import.argtypes = [C.c_char_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
+        L.ref_cameras_import.restype = C.c_int
         fp = C.POINTER(C.c_float)
         L.ref_render.argtypes = [C.c_void_p, C.c_size_t, C.c_size_t, C.c_int, C.c_int, fp, fp, fp, fp, C.c_void_p, C.c_void_p, C.c_void_p]
         L.ref_render.restype = C.c_size_t
@@ -70,6 +72,18 @@ def export_ply(in_path: str, out_path: str, import_full_sh: bool = True, export_
     rc = lib().ref_export_ply(in_path.encode(), int(import_full_sh), int(export_full_sh), out_path.encode())
     if rc:
         raise IOError(f"reference ExportPly failed ({rc}) for {in_path} -> {out_path}")
+
+
+def cameras_import(path: str):
+    """CamerasConfig::ImportJson + EstimateFloorPlane of the reference: None when ImportJson returns false, else
+    (mats [n,16] column-major, fovs [n,2], floor normal [3], floor position [3])"""
+    n = lib().ref_cameras_import(path.encode(), None, None, 0, None)
+    if n < 0:
+        return None
+    mats, fovs, floor = np.zeros((max(n, 1), 16), np.float32), np.zeros((max(n, 1), 2), np.float32), np.zeros(6, np.float32)
+    n2 = lib().ref_cameras_import(path.encode(), mats.ctypes.data, fovs.ctypes.data, max(n, 1), floor.ctypes.data)
+    assert n2 == n
+    return mats[:n], fovs[:n], floor[:3].copy(), floor[3:].copy()
 
 
 def debug_cloud() -> np.ndarray:

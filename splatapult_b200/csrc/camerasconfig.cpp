@@ -189,8 +189,14 @@ void CamerasConfig::EstimateFloorPlane(splat::vec3& normalOut, splat::vec3& posO
     float up[3] = {0.0f, 0.0f, 0.0f};
     for (const Camera& c : cameraVec)
         for (int r = 0; r < 3; r++) up[r] += weight * c.mat.at(1, r);
-    const float len = std::sqrt(up[0] * up[0] + up[1] * up[1] + up[2] * up[2]);
-    if (len > 0.0f) { up[0] /= len; up[1] /= len; up[2] /= len; }
+    // SafeNormalize (src/core/util.cpp:128-139) -> glm::normalize = v * inversesqrt(dot(v, v)): multiply by the reciprocal,
+    // not divide by the length (1 ulp apart; tests/test_ref_pin.py holds this to the reference's source bit for bit)
+    const float len2 = up[0] * up[0] + up[1] * up[1] + up[2] * up[2];
+    if (std::sqrt(len2) > 0.0f)
+    {
+        const float inv = 1.0f / std::sqrt(len2);
+        up[0] *= inv; up[1] *= inv; up[2] *= inv;
+    }
     else { up[0] = 0.0f; up[1] = 1.0f; up[2] = 0.0f; }
     float dist = 0.0f;
     for (const Camera& c : cameraVec) dist += weight * (c.mat.at(3, 0) * up[0] + c.mat.at(3, 1) * up[1] + c.mat.at(3, 2) * up[2]);

@@ -1,6 +1,6 @@
 """CamerasConfig: INRIA cameras.json -> the cameraMat values SplatRenderer::Sort/Render take.
-Checked against a numpy restatement of src/camerasconfig.cpp:31-56 (the reference's reader needs nlohmann-json,
-which is not in the image, so it cannot join oracle/_ref)."""
+Checked against a numpy restatement of src/camerasconfig.cpp:31-56; tests/test_ref_pin.py additionally holds the class
+bit for bit to the reference's own camerasconfig.cpp (compiled into oracle/_ref against a stand-in for nlohmann-json)."""
 import json
 import math
 

@@ -184,3 +184,77 @@ def test_export_ply_is_the_references(ref, splat, scratch):
     a_g, _ = ref.import_ply(got_path, False)
     np.testing.assert_array_equal(a_g[:, :16], a_w[:, :16])
     np.testing.assert_allclose(a_g[:, 16:25], a_w[:, 16:25], rtol=0, atol=2e-5 * np.abs(a_w[:, 16:25]).max())
+
+
+def _cameras_equal(ref, splat, path):
+    want = ref.cameras_import(path)
+    cfg = splat.CamerasConfig()
+    ok = cfg.ImportJson(path)
+    assert ok == (want is not None), (path, cfg.LastError())
+    if want is None:
+        return None
+    mats, fovs, nrm, pos = want
+    assert cfg.GetNumCameras() == len(mats)
+    for i in range(len(mats)):
+        m, f = cfg.GetCamera(i)
+        np.testing.assert_array_equal(m.view(np.uint32), mats[i].view(np.uint32))
+        np.testing.assert_array_equal(f.view(np.uint32), fovs[i].view(np.uint32))
+    n, p = cfg.EstimateFloorPlane()
+    np.testing.assert_array_equal(n.view(np.uint32), nrm.view(np.uint32))
+    np.testing.assert_array_equal(p.view(np.uint32), pos.view(np.uint32))
+    return want
+
+
+def test_cameras_config_is_the_references(ref, splat, scratch):
+    """CamerasConfig::ImportJson / EstimateFloorPlane (src/camerasconfig.cpp:20-96), f1: the reference's source (against a
+    stand-in for nlohmann/json) and the product agree bit for bit on every camera matrix, both fov values (fov.y from fx, as
+    the reference computes it) and the floor plane -- on the file bench.py's config 5 reads and on INRIA-shaped entries."""
+    import json
+
+    cams = scenes.ring_cameras(8, 18.0, 3.0)
+    ring = scenes.write_cameras_json(str(scratch / "pin_cameras.json"), cams, 1920, 1080, 1303.7)
+    want = _cameras_equal(ref, splat, ring)
+    assert want is not None and len(want[0]) == 8
+    entries = [{"id": 0, "img_name": "DSC_0001", "width": 1959, "height": 1090,
+                "position": [-3.0089893469241797, -0.11086489695181866, -3.7527640949141428],
+                "rotation": [[0.876134201218856, 0.06925962026449776, 0.47706599800804744],
+                             [-0.04747421839895102, 0.9972110940209488, -0.057586739349882114],
+                             [-0.4797239414934443, 0.027805376500959853, 0.8769787916452908]],
+                "fy": 1164.6601287484507, "fx": 1.1593880237791562e3},
+               {"id": 7, "width": 1.6e3, "height": 899.0, "position": [1, -2, 3e0], "rotation": [[0, 1, 0], [-1, 0, 0], [0, 0, 1]],
+                "fx": 800, "fy": 700, "extra": {"nested": [1, [2, [3]]], "s": "a\"b\u00e9"}}]
+    p = str(scratch / "pin_inria.json")
+    with open(p, "w") as f:
+        json.dump(entries, f, indent=1)
+    want = _cameras_equal(ref, splat, p)
+    assert want is not None and len(want[0]) == 2
+    # decimal strings that round differently through double -> float than straight to float would
+    p = str(scratch / "pin_rounding.json")
+    with open(p, "w") as f:
+        f.write('[{"id":1,"width":640,"height":480,"fx":500.00000000000006,"fy":1,"position":[0.1,16777217,1.00000005960464477539],'
+                '"rotation":[[0.30000001192092895508,0.7,1e-46],[4.0000000000000001e-1,0.5,0.6],[0.2,0.9,-0.0]]}]')
+    assert _cameras_equal(ref, splat, p) is not None
+    p = str(scratch / "pin_empty.json")
+    open(p, "w").write("[]")
+    want = _cameras_equal(ref, splat, p)
+    assert want is not None and len(want[0]) == 0
+
+
+@pytest.mark.parametrize("name,text", [
+    ("missing_key", '[{"id":0,"position":[1,2,3],"rotation":[[1,0,0],[0,1,0],[0,0,1]],"width":1,"height":1,"fy":1}]'),
+    ("short_position", '[{"id":0,"position":[1,2],"rotation":[[1,0,0],[0,1,0],[0,0,1]],"width":1,"height":1,"fx":1,"fy":1}]'),
+    ("string_rotation", '[{"id":0,"position":[1,2,3],"rotation":"x","width":1,"height":1,"fx":1,"fy":1}]'),
+    ("string_number", '[{"id":"0","position":[1,2,3],"rotation":[[1,0,0],[0,1,0],[0,0,1]],"width":1,"height":1,"fx":1,"fy":1}]'),
+    ("top_level_object", '{"id": 0}'),
+    ("array_of_numbers", "[1, 2, 3]"),
+    ("null_entry", "[null]"),
+    ("unterminated", "[{"),
+    ("empty_file", ""),
+    ("fy_is_optional", '[{"id":0,"position":[1,2,3],"rotation":[[1,0,0],[0,1,0],[0,0,1]],"width":4,"height":3,"fx":2}]'),
+    ("float_id", '[{"id":2.7,"position":[1,2,3],"rotation":[[1,0,0],[0,1,0],[0,0,1]],"width":4.9,"height":3.2,"fx":2,"fy":2}]'),
+])
+def test_cameras_config_decisions_are_the_references(ref, splat, scratch, name, text):
+    """accept / reject (nlohmann throws -> ImportJson returns false, camerasconfig.cpp:58-63) and, when accepted, the values"""
+    p = str(scratch / f"pin_cam_{name}.json")
+    open(p, "w").write(text)
+    _cameras_equal(ref, splat, p)
