@@ -5,7 +5,8 @@
 The reference's hot path cannot be built the normal way here (OpenGL 4.6 / GLEW / SDL2 / glm / Eigen are absent and
 its build is cmake + vcpkg), so this recipe compiles exactly the files that carry the path's arithmetic:
   * host C++   src/gaussiancloud.cpp, src/camerasconfig.cpp, src/ply.cpp, src/core/binaryattribute.cpp, src/core/log.cpp  --
-               unmodified, against oracle/ref_shim/{glm/glm.hpp, Eigen/Dense, nlohmann/json.hpp} stand-ins;
+               unmodified, against oracle/ref_shim/{glm/glm.hpp, Eigen/Dense} stand-ins and the REAL nlohmann/json 3.11.3 the image
+               carries (cudnn_frontend/thirdparty; oracle/ref_shim/nlohmann/json.hpp is the fallback stand-in);
   * GLSL       shader/presort_compute.glsl, splat_vert.glsl (4 variants: FULL_SH x FRAMEBUFFER_SRGB), splat_geom.glsl,
                splat_frag.glsl -- their text is wrapped into C++ namespaces after the mechanical rewrites below (GLSL
                declarations C++ has no syntax for) and compiled against oracle/ref_shim/glsl_shim.h.
@@ -70,6 +71,21 @@ VARIANTS = [
 ]
 
 
+def real_nlohmann_include() -> str | None:
+    """the image carries nlohmann/json 3.11.3 as a third-party header of cudnn_frontend: when it is there the reference's
+    camerasconfig.cpp is compiled against the REAL library (the reference pins `nlohmann-json` through vcpkg); the stand-in in
+    oracle/ref_shim/nlohmann is only the fallback"""
+    import sysconfig
+
+    roots = {sysconfig.get_paths().get("purelib"), sysconfig.get_paths().get("platlib")}
+    for r in roots:
+        if r:
+            d = os.path.join(r, "include", "cudnn_frontend", "thirdparty")
+            if os.path.exists(os.path.join(d, "nlohmann", "json.hpp")):
+                return d
+    return None
+
+
 def available() -> bool:
     return os.path.isdir(os.path.join(REF, "shader")) and os.path.isdir(os.path.join(REF, "src"))
 
@@ -92,8 +108,10 @@ def build(force: bool = False) -> str | None:
             f.write("// generated by oracle/build_ref.py from /root/reference/shader/*.glsl -- temporary, never committed\n")
             for fname, stage, ns, defines in VARIANTS:
                 f.write(glsl_to_cpp(open(os.path.join(REF, "shader", fname)).read(), stage, ns, defines))
+        real_json = None if os.environ.get("SPLAT_REF_JSON_STANDIN") else real_nlohmann_include()
+        json_flags = ["-I", real_json, "-DREF_REAL_NLOHMANN=1"] if real_json else []  # searched before ref_shim: <nlohmann/json.hpp> is the real one
         cmd = ["g++", "-std=c++17", "-O2", "-fPIC", "-shared", "-ffp-contract=off", "-fno-fast-math", "-fvisibility=hidden", "-march=x86-64-v2",
-               "-DNDEBUG", "-w", "-I", os.path.join(HERE, "ref_shim"), "-I", os.path.join(REF, "src"), "-I", tmp,
+               "-DNDEBUG", "-w"] + json_flags + ["-I", os.path.join(HERE, "ref_shim"), "-I", os.path.join(REF, "src"), "-I", tmp,
                os.path.join(HERE, "ref_harness.cpp")] + srcs + ["-o", LIB]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode:

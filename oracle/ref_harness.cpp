@@ -55,6 +55,16 @@ glm::vec3 SafeNormalize(const glm::vec3& v, const glm::vec3& ifZero)
     return len > 0.0f ? glm::normalize(v) : ifZero;
 }
 
+// 1: camerasconfig.cpp was compiled against the real nlohmann/json found in the image, 0: against oracle/ref_shim/nlohmann
+REF_API int ref_json_is_real()
+{
+#ifdef REF_REAL_NLOHMANN
+    return 1;
+#else
+    return 0;
+#endif
+}
+
 // CamerasConfig::ImportJson (src/camerasconfig.cpp:20-67) + EstimateFloorPlane (:69-96), executed by the reference's source.
 // mats: 16 floats per camera, column-major (glm layout); fovs: 2 per camera; floor: normal[3] then position[3]
 REF_API int ref_cameras_import(const char* path, float* mats, float* fovs, size_t capCameras, float* floor6)
@@ -83,6 +93,15 @@ REF_API int ref_cameras_import(const char* path, float* mats, float* fovs, size_
         floor6[0] = nrm.x; floor6[1] = nrm.y; floor6[2] = nrm.z; floor6[3] = pos.x; floor6[4] = pos.y; floor6[5] = pos.z;
     }
     return (int)v.size();
+}
+
+// what a caller sees after ImportJson, successful or not: the return value and how many cameras the object then holds (the
+// reference emplaces per entry, so the entries before a bad one stay)
+REF_API int ref_cameras_import_state(const char* path, int* ok)
+{
+    CamerasConfig cc;
+    *ok = cc.ImportJson(path) ? 1 : 0;
+    return (int)cc.GetNumCameras();
 }
 
 // GaussianCloud::PruneSplats (src/gaussiancloud.cpp:581-626) on an imported file: the kept records, in the reference's order

@@ -74,6 +74,23 @@ def export_ply(in_path: str, out_path: str, import_full_sh: bool = True, export_
         raise IOError(f"reference ExportPly failed ({rc}) for {in_path} -> {out_path}")
 
 
+def json_is_real() -> bool:
+    """True when the reference's camerasconfig.cpp was compiled against the real nlohmann/json (found in the image)"""
+    L = lib()
+    L.ref_json_is_real.restype = C.c_int
+    return bool(L.ref_json_is_real())
+
+
+def cameras_import_state(path: str):
+    """(ImportJson's return value, cameras held afterwards) -- the reference keeps the entries read before a bad one"""
+    L = lib()
+    L.ref_cameras_import_state.argtypes = [C.c_char_p, C.POINTER(C.c_int)]
+    L.ref_cameras_import_state.restype = C.c_int
+    ok = C.c_int()
+    n = L.ref_cameras_import_state(path.encode(), C.byref(ok))
+    return bool(ok.value), n
+
+
 def cameras_import(path: str):
     """CamerasConfig::ImportJson + EstimateFloorPlane of the reference: None when ImportJson returns false, else
     (mats [n,16] column-major, fovs [n,2], floor normal [3], floor position [3])"""

@@ -94,3 +94,37 @@ def test_deeply_nested_json_is_refused_not_a_stack_overflow(splat, scratch):
         cfg = splat.CamerasConfig()
         assert not cfg.ImportJson(str(p))
         assert "nesting" in cfg.LastError()
+
+
+def test_entries_before_a_bad_one_stay(splat, scratch):
+    """camerasconfig.cpp:55 emplaces per entry inside the try block: a type error in entry 2 returns false with entry 1 kept"""
+    good = '{"id":0,"position":[1,2,3],"rotation":[[1,0,0],[0,1,0],[0,0,1]],"width":4,"height":3,"fx":2,"fy":2}'
+    bad = '{"id":1,"position":[1,2,3],"rotation":[[1,0,0],[0,1,0],[0,0,1]],"width":4,"height":3,"fy":2}'
+    path = str(scratch / "partial.json")
+    with open(path, "w") as f:
+        f.write(f"[{good},{bad},{good}]")
+    cfg = splat.CamerasConfig()
+    assert not cfg.ImportJson(path) and cfg.GetNumCameras() == 1 and "fx" in cfg.LastError()
+    # a SYNTAX error anywhere leaves nothing: the document is parsed before the first entry is read
+    with open(path, "w") as f:
+        f.write(f"[{good},{good}")
+    cfg = splat.CamerasConfig()
+    assert not cfg.ImportJson(path) and cfg.GetNumCameras() == 0
+
+
+@pytest.mark.parametrize("text,count", [("null", 0), ('﻿[]', 0),
+                                        ('{"b":{"id":1,"position":[9,9,9],"rotation":[[1,0,0],[0,1,0],[0,0,1]],"width":4,"height":3,"fx":2,"fy":2},'
+                                         '"a":{"id":0,"position":[1,2,3],"rotation":[[1,0,0],[0,1,0],[0,0,1]],"width":4,"height":3,"fx":true,"fy":2}}', 2)])
+def test_documents_nlohmann_iterates(splat, scratch, text, count):
+    """`for (auto&& o : data)`: null iterates nothing, an object iterates its values in key order; a byte-order mark is skipped;
+    a boolean converts like a number (get<float>() of true is 1.0f)"""
+    path = str(scratch / "iter.json")
+    with open(path, "w", encoding="utf-8") as f:
+        f.write(text)
+    cfg = splat.CamerasConfig()
+    assert cfg.ImportJson(path), cfg.LastError()
+    assert cfg.GetNumCameras() == count
+    if count == 2:
+        m0, f0 = cfg.GetCamera(0)
+        np.testing.assert_array_equal(m0[12:15], [1, 2, 3])  # key "a" first
+        assert f0[0] == np.float32(2 * math.atan(np.float32(4) / np.float32(2.0)))  # fx = true -> 1.0f: 2 atan(4 / (2 * 1))

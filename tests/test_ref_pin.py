@@ -258,3 +258,59 @@ def test_cameras_config_decisions_are_the_references(ref, splat, scratch, name, 
     p = str(scratch / f"pin_cam_{name}.json")
     open(p, "w").write(text)
     _cameras_equal(ref, splat, p)
+
+
+def test_cameras_config_differential_fuzz(ref, splat, scratch):
+    """2500 mutations of a valid cameras.json (byte edits, token splices, truncations): the product's reader and the
+    reference's camerasconfig.cpp -- run against the real nlohmann/json when the image has it -- make the same accept / reject
+    decision, hold the same number of cameras afterwards (the entries before a bad one stay) and, when they accept, the same
+    values bit for bit."""
+    import json
+
+    cams = scenes.ring_cameras(3, 7.0, 1.5)
+    base = open(scenes.write_cameras_json(str(scratch / "fuzz_base.json"), cams, 1280, 720, 900.5), "rb").read()
+    rng = np.random.default_rng(77)
+    tokens = [b"null", b"true", b"false", b"[]", b"{}", b"-0", b"1e5", b"1E-3", b"0.5", b"01", b"+1", b"1.", b".5", b"1e", b"NaN", b"Infinity", b"1e999", b"-1e-999",
+              b"18446744073709551616", b"-9223372036854775809", b"4294967297", b'"x"', b'"\\u00e9"', b'"\\ud83d\\ude00"', b'"\\ud83d"', b'"\\x"', b'"\t"',
+              b"\xc3\xa9", b'"\xc3\xa9"', b'"\xc3"', b'"\xed\xa0\x80"', b'"\xf4\x90\x80\x80"', b",", b":", b"[", b"]", b"{", b"}", b'"', b"\\", b" ", b"\n", b"\xef\xbb\xbf", b"/*c*/", b"//c\n",
+              b'"id":', b'"fx":', b'"position":', b'"rotation":', b'"width":', b'"id":7,']
+    differ = []
+    path = str(scratch / "fuzz_case.json")
+    for it in range(2500):
+        buf = bytearray(base)
+        for _ in range(int(rng.integers(1, 4))):
+            kind = int(rng.integers(0, 6))
+            pos = int(rng.integers(0, len(buf) + 1))
+            if kind == 0 and len(buf):
+                buf[min(pos, len(buf) - 1)] = int(rng.integers(0, 256))
+            elif kind == 1:
+                buf[pos:pos] = tokens[int(rng.integers(0, len(tokens)))]
+            elif kind == 2 and len(buf):
+                end = min(len(buf), pos + int(rng.integers(1, 12)))
+                del buf[pos:end]
+            elif kind == 3:
+                end = min(len(buf), pos + int(rng.integers(1, 8)))
+                buf[pos:end] = tokens[int(rng.integers(0, len(tokens)))]
+            elif kind == 4:
+                del buf[pos:]
+            else:  # replace a whole number with a token
+                import re
+                nums = list(re.finditer(rb"-?\d+(\.\d+)?([eE][-+]?\d+)?", bytes(buf)))
+                if nums:
+                    m = nums[int(rng.integers(0, len(nums)))]
+                    buf[m.start():m.end()] = tokens[int(rng.integers(0, len(tokens)))]
+        open(path, "wb").write(bytes(buf))
+        ok_ref, n_ref = ref.cameras_import_state(path)
+        cfg = splat.CamerasConfig()
+        ok = cfg.ImportJson(path)
+        if ok != ok_ref or cfg.GetNumCameras() != n_ref:
+            differ.append((it, bytes(buf), ok_ref, n_ref, ok, cfg.GetNumCameras(), cfg.LastError()))
+            continue
+        if ok and n_ref:
+            mats, fovs, nrm, pos3 = ref.cameras_import(path)
+            for i in range(n_ref):
+                m, f = cfg.GetCamera(i)
+                if not (np.array_equal(m.view(np.uint32), mats[i].view(np.uint32)) and np.array_equal(f.view(np.uint32), fovs[i].view(np.uint32))):
+                    differ.append((it, bytes(buf), "values", i))
+                    break
+    assert not differ, (len(differ), differ[:3])
