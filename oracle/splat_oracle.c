@@ -290,8 +290,11 @@ static int ply_parse(const char* path, orc_ply* out)
     if (!ply_next_line(f, line, sizeof line) || strcmp(line, "ply") != 0) goto done;
     if (!ply_next_line(f, line, sizeof line) || strcmp(line, "format binary_little_endian 1.0") != 0) goto done;
     if (!ply_next_line(f, line, sizeof line)) goto done;
+    /* ply.cpp:176-209: ONE istringstream and three tokens for all header lines -- an extraction that finds nothing leaves
+     * the token as it was (sscanf does the same with unmatched %s), so a blank line repeats the previous property line and
+     * "property float" re-uses the previous name */
+    char t1[64] = "", t2[64] = "", t3[64] = "";
     {
-        char t1[64], t2[64];
         unsigned long long cnt;
         if (sscanf(line, "%63s %63s %llu", t1, t2, &cnt) != 3 || strcmp(t1, "element") || strcmp(t2, "vertex")) goto done;
         out->vertexCount = (size_t)cnt;
@@ -300,7 +303,6 @@ static int ply_parse(const char* path, orc_ply* out)
     for (;;) {
         if (!ply_next_line(f, line, sizeof line)) goto done;
         if (!strcmp(line, "end_header")) break;
-        char t1[64] = "", t2[64] = "", t3[64] = "";
         sscanf(line, "%63s %63s %63s", t1, t2, t3);
         if (strcmp(t1, "property")) goto done; /* ply.cpp:209-213: anything else is an error */
         int ty = ply_type_from_token(t2);
@@ -311,7 +313,7 @@ static int ply_parse(const char* path, orc_ply* out)
         }
         orc_prop* p = &out->props[out->nprops++];
         memset(p, 0, sizeof *p);
-        strncpy(p->name, t3, sizeof p->name - 1);
+        memcpy(p->name, t3, sizeof p->name - 1); /* both 64 bytes, t3 is NUL-terminated within 63 */
         p->attr.type = ty;
         p->attr.size = k_type_size[ty];
         p->attr.offset = out->vertexSize; /* ply.cpp:106-112 AddProperty */
@@ -348,7 +350,9 @@ ORC_API int orc_import_ply(const char* path, int import_full_sh, size_t* n_out, 
     int rc = ply_parse(path, &ply);
     if (rc) return rc;
     orc_attr ax, ay, az, adc[3], arest[45], aop, asc[3], arot[4];
-    ply_get(&ply, "x", &ax); ply_get(&ply, "y", &ay); ply_get(&ply, "z", &az);
+    /* gaussiancloud.cpp:174-176: !Get(x) || !Get(y) || !Get(z) short-circuits -- nothing after the first missing one is looked up */
+    memset(&ax, 0, sizeof ax); memset(&ay, 0, sizeof ay); memset(&az, 0, sizeof az);
+    if (ply_get(&ply, "x", &ax) && ply_get(&ply, "y", &ay)) ply_get(&ply, "z", &az);
     char nm[32];
     for (int i = 0; i < 3; i++) { snprintf(nm, sizeof nm, "f_dc_%d", i); ply_get(&ply, nm, &adc[i]); }
     int full = 0;

@@ -169,7 +169,9 @@ struct PlyProps
 PlyProps LookupProps(const Ply& ply, bool wantFullSH)
 {
     PlyProps p;
-    ply.GetProperty("x", p.px); ply.GetProperty("y", p.py); ply.GetProperty("z", p.pz);
+    // `!Get("x") || !Get("y") || !Get("z")` in the reference (gaussiancloud.cpp:174-176) short-circuits: after a missing x
+    // neither y nor z is looked up, after a missing y not z -- they then read as zero like any missing property
+    if (ply.GetProperty("x", p.px) && ply.GetProperty("y", p.py)) ply.GetProperty("z", p.pz);
     ply.GetProperty("opacity", p.opacity);
     for (int i = 0; i < 3; i++) ply.GetProperty("f_dc_" + std::to_string(i), p.dc[i]);
     for (int i = 0; i < 3; i++) ply.GetProperty("scale_" + std::to_string(i), p.scale[i]);

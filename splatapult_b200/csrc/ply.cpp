@@ -1,8 +1,9 @@
 // ply.cpp -- binary_little_endian PLY, vertex element only.
 // Accept/reject behaviour follows the reference reader (src/ply.cpp:140-254): the first three non-comment
 // lines must be exactly "ply", "format binary_little_endian 1.0", "element vertex <N>"; then only
-// "property <type> <name>" lines until "end_header"; LF line ends (a stray '\r' makes a line mismatch);
+// "property <type> <name>" lines until "end_header"; LF line ends (a stray '\r' makes a keyword line mismatch);
 // no list properties; property offsets accumulate in declaration order; the body is N*vertexSize bytes.
+// Held to the reference's own ply.cpp by a differential fuzz (tests/test_ref_pin.py), accidents included: see ParseHeader.
 #include "splatapult_b200/ply.h"
 
 #include <algorithm>
@@ -56,26 +57,28 @@ bool Ply::ParseHeader(std::istream& in)
         return false;
     }
     if (!NextLine(in, line)) { error = "truncated header"; return false; }
+    // One stream and three tokens for every header line, as in the reference (ply.cpp:176-209): an extraction that finds
+    // nothing leaves its token AS IT WAS.  So a blank (or "\r"-only) line after a property line repeats that property -- its
+    // size is added again, the name keeps its first offset -- and "property float" re-uses the previous name.  The reference's
+    // own reader accepts such files and lays the vertex out that way (tests/test_ref_pin.py, differential fuzz).
+    std::istringstream iss(line);
+    std::string token1, token2, token3;
+    if (!((iss >> token1 >> token2 >> vertexCount) && token1 == "element" && token2 == "vertex"))
     {
-        std::istringstream iss(line);
-        std::string kw, what;
-        if (!(iss >> kw >> what >> vertexCount) || kw != "element" || what != "vertex")
-        {
-            error = "expected \"element vertex <count>\"";
-            return false;
-        }
+        error = "expected \"element vertex <count>\"";
+        return false;
     }
     for (;;)
     {
         if (!NextLine(in, line)) { error = "missing end_header"; return false; }
         if (line == "end_header") return true;
-        std::istringstream iss(line);
-        std::string kw, typeTok, name;
-        iss >> kw >> typeTok >> name;
-        if (kw != "property") { error = "expected a property line, got \"" + line + "\""; return false; }
-        const Type type = TypeFromToken(typeTok);
-        if (type == Type::Unknown) { error = "unsupported property type \"" + typeTok + "\""; return false; }
-        AddProperty(name, type);
+        iss.str(line);
+        iss.clear();
+        iss >> token1 >> token2 >> token3;
+        if (token1 != "property") { error = "expected a property line, got \"" + line + "\""; return false; }
+        const Type type = TypeFromToken(token2);
+        if (type == Type::Unknown) { error = "unsupported property type \"" + token2 + "\""; return false; }
+        AddProperty(token3, type);
     }
 }
 

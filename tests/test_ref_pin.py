@@ -314,3 +314,129 @@ def test_cameras_config_differential_fuzz(ref, splat, scratch):
                     differ.append((it, bytes(buf), "values", i))
                     break
     assert not differ, (len(differ), differ[:3])
+
+
+def _ref_import_isolated(ref, path, full):
+    """the reference's ImportPly in a forked child with an address-space limit: a header that claims 10^11 vertices makes the
+    reference throw bad_alloc out of `new` (the application dies); the test must survive that and call it a crash"""
+    import pickle
+    import resource
+    import struct
+
+    import warnings
+
+    r, w = os.pipe()
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore", DeprecationWarning)  # "fork() in a multi-threaded process": the child only runs the reference and _exit()s
+        pid = os.fork()
+    if pid == 0:
+        code = 1
+        try:
+            os.close(r)
+            resource.setrlimit(resource.RLIMIT_AS, (4 << 30, 4 << 30))
+            devnull = os.open(os.devnull, os.O_WRONLY)
+            os.dup2(devnull, 1)
+            os.dup2(devnull, 2)
+            try:
+                aos, f = ref.import_ply(path, full)
+                out = pickle.dumps(("ok", aos.shape, bool(f), aos.tobytes()))
+            except IOError:
+                out = pickle.dumps(("reject",))
+            out = struct.pack("<Q", len(out)) + out
+            k = 0
+            while k < len(out):
+                k += os.write(w, out[k:k + 65536])
+            code = 0
+        finally:
+            os._exit(code)
+    os.close(w)
+    data = b""
+    while True:
+        c = os.read(r, 1 << 20)
+        if not c:
+            break
+        data += c
+    os.close(r)
+    os.waitpid(pid, 0)
+    if len(data) < 8 or len(data) - 8 != struct.unpack("<Q", data[:8])[0]:
+        return ("crash",)
+    return pickle.loads(data[8:])
+
+
+def test_ply_reader_differential_fuzz(ref, splat, oracle, scratch):
+    """1500 header mutations of a valid INRIA file (byte edits, spliced / deleted / duplicated lines, blank and CR lines,
+    typed extras): the reference's own ply.cpp + gaussiancloud.cpp, the oracle and the product take the same accept / reject
+    decision, the same vertex count, stride and SH mode and decode the same AoS bytes -- including the reference's accidents
+    (a blank header line repeats the property before it; after a missing x neither y nor z is looked up; the first of two
+    equally named properties wins).  Left out of the VALUE comparison, not of the decision: headers that give an INRIA
+    property a non-float type (the reference type-puns the bytes in release builds and asserts in debug builds; oracle and
+    product read zero) and vertex counts above 64 (the body behind the header is 64 records + zero padding; beyond the file
+    the reference reads uninitialised memory).  The reference runs in a forked child: huge counts kill it (bad_alloc)."""
+    import re
+
+    base_path = str(scratch / "fuzz_base.ply")
+    scenes.write_synthetic_ply(base_path, 8, 3, seed=3)
+    with open(base_path, "rb") as fh:
+        base = fh.read()
+    hdr_end = base.index(b"end_header\n") + 11
+    tail = bytes(96 * 1024)  # zero padding: a mutated header may claim more / larger vertices than the 8 that are there
+    schema = {"x", "y", "z", "opacity"} | {f"f_dc_{i}" for i in range(3)} | {f"f_rest_{i}" for i in range(45)} | {f"scale_{i}" for i in range(3)} | {f"rot_{i}" for i in range(4)}
+    tokens = [b"property float x\n", b"property double x\n", b"property uchar red\n", b"property list uchar int vi\n", b"element face 0\n", b"element vertex 3\n",
+              b"comment hi\n", b"format ascii 1.0\n", b"format binary_big_endian 1.0\n", b"end_header\n", b"property float\n", b"property half q\n", b"property int8 a\n",
+              b"property uint16 b\n", b"property int c\n", b"property float32 f_dc_0\n", b"\r\n", b" ", b"\n", b"\t", b"0", b"-1", b"99999999999", b"ply\n", b"obj_info x\n",
+              b"property float64 opacity\n", b"property short scale_0\n", b"property\n", b"property double\n", b"\n\n", b"comment\n", b"property float y\n"]
+    rng = np.random.default_rng(11)
+    differ, stats = [], {"accept": 0, "reject": 0, "crash": 0, "values_skipped": 0}
+    path = str(scratch / "fuzz_case.ply")
+    for it in range(1500):
+        hdr = bytearray(base[:hdr_end])
+        for _ in range(int(rng.integers(1, 3))):
+            kind = int(rng.integers(0, 5))
+            pos = int(rng.integers(0, len(hdr)))
+            if kind == 0:
+                hdr[pos] = int(rng.integers(0, 256))
+            elif kind == 1:
+                hdr[pos:pos] = tokens[int(rng.integers(0, len(tokens)))]
+            elif kind == 2:
+                del hdr[pos:pos + int(rng.integers(1, 20))]
+            elif kind == 3:  # delete a whole line
+                ls, le = bytes(hdr).rfind(b"\n", 0, pos) + 1, bytes(hdr).find(b"\n", pos) + 1
+                if le > ls:
+                    del hdr[ls:le]
+            else:  # a token at a line start
+                ls = bytes(hdr).rfind(b"\n", 0, pos) + 1
+                hdr[ls:ls] = tokens[int(rng.integers(0, len(tokens)))]
+        with open(path, "wb") as fh:
+            fh.write(bytes(hdr) + base[hdr_end:] + tail)
+        full = bool(rng.integers(0, 2))
+        want = _ref_import_isolated(ref, path, full)
+        gc = splat.GaussianCloud(import_full_sh=full)
+        ok = gc.ImportPly(path)
+        try:
+            a_or, f_or = oracle.import_ply(path, full)
+            ok_or = True
+        except Exception:  # noqa: BLE001
+            ok_or = False
+        if want[0] == "crash":
+            stats["crash"] += 1
+            continue
+        if (want[0] == "ok") != ok or (want[0] == "ok") != ok_or:
+            differ.append((it, "decision", want[0], ok, ok_or, bytes(hdr)[-300:]))
+            continue
+        if not ok:
+            stats["reject"] += 1
+            continue
+        stats["accept"] += 1
+        _, shape, f_ref, raw = want
+        a = gc.GetRawData()
+        if a.shape != tuple(shape) or gc.HasFullSH() != f_ref or a_or.shape != tuple(shape) or f_or != f_ref:
+            differ.append((it, "shape / SH mode", shape, f_ref, a.shape, gc.HasFullSH(), a_or.shape, f_or))
+            continue
+        typed = [m for m in re.finditer(rb"property[ \t]+(\S+)[ \t]+(\S+)", bytes(hdr)) if m.group(2).decode("latin1") in schema and m.group(1) not in (b"float", b"float32")]
+        if typed or shape[0] > 64 or b"property double\n" in bytes(hdr) or b"property\n" in bytes(hdr):
+            stats["values_skipped"] += 1  # (the name-less tokens re-use the previous name with another type)
+            continue
+        if a.tobytes() != raw or a_or.tobytes() != raw:
+            differ.append((it, "values", "product" if a.tobytes() != raw else "oracle", bytes(hdr)[-300:]))
+    assert not differ, (len(differ), stats, differ[:3])
+    assert stats["accept"] > 200 and stats["reject"] > 400, stats
