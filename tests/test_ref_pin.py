@@ -440,3 +440,43 @@ def test_ply_reader_differential_fuzz(ref, splat, oracle, scratch):
             differ.append((it, "values", "product" if a.tobytes() != raw else "oracle", bytes(hdr)[-300:]))
     assert not differ, (len(differ), stats, differ[:3])
     assert stats["accept"] > 200 and stats["reject"] > 400, stats
+
+
+def test_random_extreme_scenes(ref, oracle, scratch):
+    """300 small random scenes through the reference's shader source and the oracle: huge / sub-pixel / needle-shaped
+    splats, saturated and vanishing opacities, cameras inside the cloud, far away and off-axis, narrow and very wide fields
+    of view, odd viewport sizes, both SH degrees, sRGB mode -- records, draw order and framebuffer bit for bit."""
+    rng = np.random.default_rng(20260924)
+    frames = drawn = 0
+    path = str(scratch / "pin_random.ply")
+    for it in range(300):
+        n, deg = int(rng.integers(1, 120)), int(rng.choice([0, 3]))
+        a = scenes.synthetic_cloud_arrays(n, deg, seed=int(rng.integers(0, 1 << 30)), half_extent=float(rng.choice([0.5, 2.0, 6.0])))
+        k = int(rng.integers(0, 5))
+        if k == 0:
+            a["log_scale"][: n // 3] += rng.uniform(1.5, 5.0)
+        elif k == 1:
+            a["log_scale"][: n // 3] -= rng.uniform(3.0, 9.0)
+        elif k == 2:
+            a["log_scale"][:, 0] -= 8.0
+        elif k == 3:
+            a["opacity"][: n // 2] = rng.choice([-12.0, 12.0, 0.0, -5.54])
+        scenes.write_ply_from_arrays(path, a)
+        aos, full = ref.import_ply(path, True)
+        w, h = [(64, 48), (97, 33), (33, 97), (160, 120)][int(rng.integers(0, 4))]
+        ck = int(rng.integers(0, 5))
+        if ck == 0:
+            cam = scenes.translate(float(rng.normal()), float(rng.normal()), float(rng.uniform(0.2, 12)))
+        elif ck == 1:
+            cam = scenes.look_at_camera(tuple(rng.normal(size=3) * 3), (0, 0, 0))
+        elif ck == 2:
+            cam = scenes.look_at_camera(tuple(rng.normal(size=3) * 0.3), tuple(rng.normal(size=3)))
+        elif ck == 3:
+            cam = scenes.look_at_camera((0, 0, 40.0), (0, 0, 0))
+        else:
+            cam = scenes.look_at_camera(tuple(rng.normal(size=3) * 8), tuple(rng.normal(size=3) * 2))
+        proj = scenes.perspective(float(rng.choice([scenes.FOVY, 0.3, 2.4])), w / h)
+        fb, rec, order = _same_frame(ref, oracle, aos, full, cam, proj, w, h, srgb=bool(rng.integers(0, 2)) and deg == 3)
+        frames += 1
+        drawn += len(order)
+    assert frames == 300 and drawn > 3000
