@@ -18,6 +18,8 @@ class SPLAT_CPP_API CamerasConfig
 public:
     CamerasConfig() = default;
 
+    // false on a missing file, malformed JSON or a missing / non-numeric field -- the decisions nlohmann/json makes for the
+    // reference (tests/test_ref_pin.py); entries read before a bad one stay in the list, as the reference's emplace_back leaves them
     bool ImportJson(const std::string& jsonFilename);
 
     const std::vector<Camera>& GetCameraVec() const { return cameraVec; }
