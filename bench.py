@@ -580,7 +580,7 @@ def run_workload(rig: Rig, name: str, cam, steps: int, warmup: int, *, headline:
         "exact_mode": {"ms_per_step": exact_ms, "value": n * world / (exact_ms * 1e-3) / 1e6, "unit": "Msplats/s",
                        "note": "early_out_T = 0: every list entry of every pixel is blended, as the reference does"},
         "parity": par,
-        "visible": v, "tile_instances": d, "sort_bits": int(st.sort_bits), "sort_passes": int(st.sort_passes),
+        "visible": v, "tile_instances": d, "tile_px": f"{int(st.tile_w)}x{int(st.tile_h)}", "sort_bits": int(st.sort_bits), "sort_passes": int(st.sort_passes),
         "stage_ms": {k: float(x) for k, x in stage.items()}, "stage_gbs": stage_gbs,
         "sort_gkeys_per_s": (d / ((stages[1] + stages[2]) * 1e-3) / 1e9) if (stages[1] + stages[2]) > 0 else None,
         "load_s": load_s, "broadcast_ms": broadcast_ms, "fp16_target": w["fp16"],
@@ -676,7 +676,7 @@ def run_ours(args, rank, local_rank, world):
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": workload_string(head),
                    "l2": "flushed between timed frames (256 MiB memset, untimed); e2e loop: per-frame working set > L2",
-                   "tile": 16, "early_out_T": EARLY_OUT_T, "sort": args.sort_mode + sort_desc, "sort_bits": main["sort_bits"], "sort_passes": main["sort_passes"],
+                   "tile": main["tile_px"], "early_out_T": EARLY_OUT_T, "sort": args.sort_mode + sort_desc, "sort_bits": main["sort_bits"], "sort_passes": main["sort_passes"],
                    "visible": main["visible"], "tile_instances": main["tile_instances"], "parallelism": f"views x{world}",
                    "views": "rank 0: the BASELINE camera; rank r > 0: look-at camera on a ring of the same radius" if world > 1 else "the BASELINE camera",
                    "numa_node": rig.numa_node, "nccl": sp.SplatComm.NcclVersion() if world > 1 else None},
