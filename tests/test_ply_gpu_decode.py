@@ -130,3 +130,57 @@ def test_init_from_ply_renders_the_same_frame(splat, golden_dir):
     assert rb.GetStats().num_gaussians == gc.GetNumGaussians()
     with pytest.raises(api.SplatError):
         splat.SplatRenderer().InitFromPly(os.path.join(golden_dir, "does_not_exist.ply"))
+
+
+@pytest.mark.gpu
+def test_gpu_decode_equals_host_decode_on_mutated_headers(splat, scratch):
+    """400 header mutations of a valid INRIA file (the family tests/test_ref_pin.py runs against the reference's own reader):
+    the CUDA decode takes the host decode's decision and produces its bytes -- repeated / typed / missing properties, vertex
+    sizes that are no multiple of four (byte loads), stale-token lines, claimed counts beyond the body (zero rows)."""
+    base_path = str(scratch / "gpufuzz_base.ply")
+    scenes.write_synthetic_ply(base_path, 37, 3, seed=13)
+    with open(base_path, "rb") as fh:
+        base = fh.read()
+    hdr_end = base.index(b"end_header\n") + 11
+    tail = bytes(64 * 1024)
+    tokens = [b"property float x\n", b"property double x\n", b"property uchar red\n", b"property list uchar int vi\n", b"element face 0\n", b"element vertex 3\n",
+              b"element vertex 41\n", b"comment hi\n", b"format ascii 1.0\n", b"end_header\n", b"property float\n", b"property int8 a\n", b"property uint16 b\n", b"property int c\n",
+              b"property float32 f_dc_0\n", b"\r\n", b" ", b"\n", b"\t", b"0", b"1", b"ply\n", b"property float64 opacity\n", b"property short scale_0\n", b"property\n",
+              b"property double\n", b"\n\n", b"property float y\n", b"property uchar q\nproperty uchar r\nproperty uchar s\n"]
+    rng = np.random.default_rng(17)
+    path = str(scratch / "gpufuzz_case.ply")
+    accepted = odd = 0
+    for it in range(400):
+        hdr = bytearray(base[:hdr_end])
+        for _ in range(int(rng.integers(1, 3))):
+            kind, pos = int(rng.integers(0, 5)), int(rng.integers(0, len(hdr)))
+            if kind == 0:
+                hdr[pos] = int(rng.integers(0, 256))
+            elif kind == 1:
+                hdr[pos:pos] = tokens[int(rng.integers(0, len(tokens)))]
+            elif kind == 2:
+                del hdr[pos:pos + int(rng.integers(1, 20))]
+            elif kind == 3:
+                ls, le = bytes(hdr).rfind(b"\n", 0, pos) + 1, bytes(hdr).find(b"\n", pos) + 1
+                if le > ls:
+                    del hdr[ls:le]
+            else:
+                ls = bytes(hdr).rfind(b"\n", 0, pos) + 1
+                hdr[ls:ls] = tokens[int(rng.integers(0, len(tokens)))]
+        m = re.search(rb"element vertex (\d+)", bytes(hdr))
+        if m and int(m.group(1)) > 4096:
+            continue  # keep the scratch files small; huge counts are test_host_cloud's business
+        with open(path, "wb") as fh:
+            fh.write(bytes(hdr) + base[hdr_end:] + tail)
+        full = bool(rng.integers(0, 2))
+        host, dev = splat.GaussianCloud(import_full_sh=full), splat.GaussianCloud(import_full_sh=full)
+        ok_h, ok_d = host.ImportPly(path), dev.ImportPlyGpu(path)
+        assert ok_h == ok_d, (it, bytes(hdr)[-200:])
+        if not ok_h:
+            continue
+        accepted += 1
+        assert host.HasFullSH() == dev.HasFullSH() and host.GetNumGaussians() == dev.GetNumGaussians()
+        a, b = host.GetRawData(), dev.GetRawData()
+        np.testing.assert_array_equal(a.view(np.uint32), b.view(np.uint32), err_msg=f"case {it}")
+        odd += int(b"uchar" in bytes(hdr) or b"int8" in bytes(hdr) or b"uint16" in bytes(hdr) or b"short" in bytes(hdr))
+    assert accepted > 80 and odd > 10, (accepted, odd)
