@@ -181,6 +181,10 @@ def test_gpu_decode_equals_host_decode_on_mutated_headers(splat, scratch):
         accepted += 1
         assert host.HasFullSH() == dev.HasFullSH() and host.GetNumGaussians() == dev.GetNumGaussians()
         a, b = host.GetRawData(), dev.GetRawData()
-        np.testing.assert_array_equal(a.view(np.uint32), b.view(np.uint32), err_msg=f"case {it}")
+        # bit for bit, except that a NaN is a NaN: garbage read through a mutated layout overflows expf, and inf * 0 gives the
+        # x86 "indefinite" 0xFFC00000 on the host and CUDA's canonical 0x7FFFFFFF on the device
+        nan_a, nan_b = np.isnan(a), np.isnan(b)
+        np.testing.assert_array_equal(nan_a, nan_b, err_msg=f"case {it}")
+        np.testing.assert_array_equal(a.view(np.uint32)[~nan_a], b.view(np.uint32)[~nan_b], err_msg=f"case {it}")
         odd += int(b"uchar" in bytes(hdr) or b"int8" in bytes(hdr) or b"uint16" in bytes(hdr) or b"short" in bytes(hdr))
     assert accepted > 80 and odd > 10, (accepted, odd)
