@@ -104,6 +104,26 @@ REF_API int ref_cameras_import_state(const char* path, int* ok)
     return (int)cc.GetNumCameras();
 }
 
+// the sixteen BinaryAttributes of GaussianCloud::InitAttribs (src/gaussiancloud.cpp:628-657) after importing `path`:
+// out[16][3] = (type, size, offset) in the order of the accessors of src/gaussiancloud.h:42-57
+REF_API int ref_attrib_table(const char* path, int importFullSH, uint64_t* out)
+{
+    GaussianCloud::Options opt{importFullSH != 0, true};
+    GaussianCloud gc(opt);
+    if (!gc.ImportPly(path)) return -1;
+    const BinaryAttribute* a[16] = {&gc.GetPosWithAlphaAttrib(), &gc.GetR_SH0Attrib(), &gc.GetR_SH1Attrib(), &gc.GetR_SH2Attrib(), &gc.GetR_SH3Attrib(),
+                                    &gc.GetG_SH0Attrib(), &gc.GetG_SH1Attrib(), &gc.GetG_SH2Attrib(), &gc.GetG_SH3Attrib(),
+                                    &gc.GetB_SH0Attrib(), &gc.GetB_SH1Attrib(), &gc.GetB_SH2Attrib(), &gc.GetB_SH3Attrib(),
+                                    &gc.GetCov3_Col0Attrib(), &gc.GetCov3_Col1Attrib(), &gc.GetCov3_Col2Attrib()};
+    for (int i = 0; i < 16; i++)
+    {
+        out[i * 3 + 0] = (uint64_t)a[i]->type;
+        out[i * 3 + 1] = (uint64_t)a[i]->size;
+        out[i * 3 + 2] = (uint64_t)a[i]->offset;
+    }
+    return (int)gc.GetStride();
+}
+
 // GaussianCloud::PruneSplats (src/gaussiancloud.cpp:581-626) on an imported file: the kept records, in the reference's order
 REF_API int ref_prune_splats(const char* path, int importFullSH, const float* origin, uint32_t keep, size_t* n, size_t* stride, float* out, size_t capFloats)
 {

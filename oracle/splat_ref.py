@@ -81,6 +81,22 @@ def json_is_real() -> bool:
     return bool(L.ref_json_is_real())
 
 
+ATTRIB_NAMES = ("posWithAlpha", "r_sh0", "r_sh1", "r_sh2", "r_sh3", "g_sh0", "g_sh1", "g_sh2", "g_sh3", "b_sh0", "b_sh1", "b_sh2", "b_sh3",
+                "cov3_col0", "cov3_col1", "cov3_col2")
+
+
+def attrib_table(path: str, import_full_sh: bool = True):
+    """{name: (type, size, offset)} of the reference's InitAttribs after importing `path`, and its stride"""
+    L = lib()
+    L.ref_attrib_table.argtypes = [C.c_char_p, C.c_int, C.c_void_p]
+    L.ref_attrib_table.restype = C.c_int
+    out = np.zeros(48, np.uint64)
+    stride = L.ref_attrib_table(path.encode(), int(import_full_sh), out.ctypes.data)
+    if stride < 0:
+        raise IOError(f"reference ImportPly returned false for {path}")
+    return {n: tuple(int(v) for v in out[i * 3:i * 3 + 3]) for i, n in enumerate(ATTRIB_NAMES)}, stride
+
+
 def cameras_import_state(path: str):
     """(ImportJson's return value, cameras held afterwards) -- the reference keeps the entries read before a bad one"""
     L = lib()

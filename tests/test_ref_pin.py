@@ -480,3 +480,16 @@ def test_random_extreme_scenes(ref, oracle, scratch):
         frames += 1
         drawn += len(order)
     assert frames == 300 and drawn > 3000
+
+
+def test_attribute_table_is_the_references(ref, splat, golden_dir, scratch):
+    """GaussianCloud::InitAttribs (src/gaussiancloud.cpp:628-657), a1: the sixteen (type, size, offset) triples the accessors
+    of gaussiancloud.h:42-57 hand out, and the stride -- full SH, base layout, and a deg-0 file imported with importFullSH"""
+    deg0 = str(scratch / "pin_attr_deg0.ply")
+    scenes.write_synthetic_ply(deg0, 10, 0, seed=1)
+    for path, full in ((os.path.join(golden_dir, "reference_test.ply"), True), (os.path.join(golden_dir, "reference_test.ply"), False), (deg0, True)):
+        want, stride = ref.attrib_table(path, full)
+        gc = splat.GaussianCloud(import_full_sh=full)
+        assert gc.ImportPly(path) and gc.GetStride() == stride
+        for name, triple in want.items():
+            assert tuple(gc.GetAttrib(name)) == triple, (path, full, name)
