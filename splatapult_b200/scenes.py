@@ -139,3 +139,16 @@ def write_cameras_json(path: str, cams: list[np.ndarray], width: int = 1920, hei
     with open(path, "w") as f:
         json.dump(out, f)
     return path
+
+
+SPECIAL_FLOATS = np.array([0.0, -0.0, 1.0, -1.0, np.inf, -np.inf, np.nan, 1e-45, -1e-45, 1e-38, 3.4e38, -3.4e38, 88.7, -88.7, 89.0, -104.0, 16.6, -16.7, 1e-20, 0.5], np.float32)
+
+
+def poison_arrays(a, rng) -> None:
+    """parity-test helper: 15 % of every property replaced by special values (zeros, infinities, NaN, denormals, the edges of expf), 5 % by values
+    of random magnitude 1e-30 .. 1e30"""
+    for arr in a.values():
+        m = rng.random(arr.shape) < 0.15
+        arr[m] = rng.choice(SPECIAL_FLOATS, size=int(m.sum()))
+        m2 = rng.random(arr.shape) < 0.05
+        arr[m2] = (rng.standard_normal(int(m2.sum())) * 10.0 ** rng.uniform(-30, 30, int(m2.sum()))).astype(np.float32)

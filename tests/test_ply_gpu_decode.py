@@ -188,3 +188,24 @@ def test_gpu_decode_equals_host_decode_on_mutated_headers(splat, scratch):
         np.testing.assert_array_equal(a.view(np.uint32)[~nan_a], b.view(np.uint32)[~nan_b], err_msg=f"case {it}")
         odd += int(b"uchar" in bytes(hdr) or b"int8" in bytes(hdr) or b"uint16" in bytes(hdr) or b"short" in bytes(hdr))
     assert accepted > 80 and odd > 10, (accepted, odd)
+
+
+@pytest.mark.gpu
+def test_gpu_decode_of_poisoned_bodies(splat, scratch):
+    """bodies full of infinities, NaN, denormals, zero quaternions and overflowing log-scales (the family the reference's
+    source, the oracle and the host decode agree on bit for bit, tests/test_ref_pin.py): the CUDA decode produces the host
+    decode's bits; where the host has a NaN the device has a NaN (the payloads are the platforms')"""
+    rng = np.random.default_rng(4)
+    path = str(scratch / "gpu_poison.ply")
+    for it in range(100):
+        n, deg = int(rng.integers(1, 300)), int(rng.choice([0, 3]))
+        a = scenes.synthetic_cloud_arrays(n, deg, seed=int(rng.integers(0, 1 << 30)))
+        scenes.poison_arrays(a, rng)
+        scenes.write_ply_from_arrays(path, a)
+        for full in (True, False):
+            host, dev = splat.GaussianCloud(import_full_sh=full), splat.GaussianCloud(import_full_sh=full)
+            assert host.ImportPly(path) and dev.ImportPlyGpu(path) and host.HasFullSH() == dev.HasFullSH()
+            x, y = host.GetRawData(), dev.GetRawData()
+            nx, ny = np.isnan(x), np.isnan(y)
+            np.testing.assert_array_equal(nx, ny, err_msg=f"case {it}")
+            np.testing.assert_array_equal(x.view(np.uint32)[~nx], y.view(np.uint32)[~ny], err_msg=f"case {it}")
