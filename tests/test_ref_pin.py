@@ -333,7 +333,9 @@ def _ref_import_isolated(ref, path, full):
         code = 1
         try:
             os.close(r)
-            resource.setrlimit(resource.RLIMIT_AS, (4 << 30, 4 << 30))
+            with open("/proc/self/statm") as fh:  # address space already mapped (the test process may have torch loaded) + 6 GiB
+                mapped = int(fh.read().split()[0]) * os.sysconf("SC_PAGE_SIZE")
+            resource.setrlimit(resource.RLIMIT_AS, (mapped + (6 << 30), mapped + (6 << 30)))
             devnull = os.open(os.devnull, os.O_WRONLY)
             os.dup2(devnull, 1)
             os.dup2(devnull, 2)
